@@ -1,0 +1,148 @@
+"""Pin the CPU oracle (oracle/vgm_oracle.py) against golden vectors produced by the LIVE
+reference (oracle/make_golden.py), and against the live reference itself when present."""
+import os
+
+import numpy as np
+import pytest
+import sympy as sym
+
+from oracle import vgm_oracle as vo
+from oracle import reference_shim as rs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+@pytest.mark.parametrize("case", ["rbf_T40", "rbf_T120", "rq_T30"])
+def test_kernel_function_matches_reference(case):
+    g = load("kernel_function.npz")
+    t, t2 = g[case + "__t"], g[case + "__t2"]
+    D, A, C, Cobs, Cso = vo.kernel_function(t, t2, str(g[case + "__type"]), list(g[case + "__param"]))
+    assert relerr(C, g[case + "__C"]) < 1e-14
+    assert relerr(Cobs, g[case + "__Cobs"]) < 1e-14
+    assert relerr(Cso, g[case + "__Cso"]) < 1e-14
+    cond = float(g[case + "__condC"])
+    # D and A go through a solve with C: agreement is bounded by cond(C)*eps
+    tol = max(1e-12, 50 * cond * 2.2e-16)
+    assert relerr(D, g[case + "__D"]) < tol
+    assert relerr(A, g[case + "__A"]) < tol
+
+
+def test_kernel_function_default_rq_grids_only():
+    # reference default RQ [0.1,2,5] on the Lotka-Volterra grid: cond(C) ~ 1e17, so only the
+    # kernel grids (not the solve) are comparable
+    g = load("kernel_function.npz")
+    case = "rq_default_T50"
+    C, dC, ddC, Cobs, Cso = vo.kernel_matrices(g[case + "__t"], g[case + "__t2"], "RQ", list(g[case + "__param"]))
+    assert relerr(C, g[case + "__C"]) < 1e-14
+    assert relerr(Cobs, g[case + "__Cobs"]) < 1e-14
+    assert float(g[case + "__condC"]) > 1e12
+
+
+def test_kernel_function_errors():
+    with pytest.raises(ValueError):
+        vo.kernel_function([0., 1.], [0., 1.], "rbf", [1., 1.])
+    with pytest.raises(ValueError):
+        vo.kernel_function(np.zeros((2, 2)), [0., 1.], "rbf", [1., 1.])
+
+
+def _lin_from_golden(g, lines, params, zero_couplings=()):
+    names = [str(s) for s in g["names"]]
+    state = sym.symbols(names)
+    param = sym.symbols(list(params))
+    odes_sym = vo.parse_ode_lines(lines)
+    sc = [[int(v) for v in str(c).split(",") if v != ""] for c in g["couplings"]]
+    return vo.Linearisation(odes_sym, state, param, couplings=sc), names
+
+
+@pytest.mark.parametrize("fname", ["lorenz96_K10_T40.npz", "lorenz96_K12_T100.npz",
+                                   "lorenz96_K8_T30_allhidden.npz"])
+def test_lorenz96_general_and_specialised_paths(fname):
+    g = load(fname)
+    K = len(g["names"])
+    lin, names = _lin_from_golden(g, vo.lorenz96_ode_lines(K), ["_alpha"])
+    clamp = bool(g["clamp"])
+    observed = [str(s) for s in g["observed"]]
+    hidden = [u for u in range(K) if (names[u] not in observed)] if clamp else list(range(K))
+    D, A = g["D"], g["A"]
+    X = g["X0"].copy()
+    Xs = X.copy()
+    for it in range(g["thetas"].shape[0]):
+        th, m, Sc, Cth = vo.theta_step(X, lin, D, A)
+        assert relerr(th, g["thetas"][it]) < 1e-12
+        th2 = vo.lorenz96_theta_step(Xs, D, A)[0]
+        assert relerr(th2, g["thetas"][it]) < 1e-12
+        X, _ = vo.state_sweep(X, [8.0], lin, D, hidden)          # strict: literal theta* = 8
+        Xs = vo.lorenz96_state_sweep(Xs, 8.0, D, hidden)
+        assert relerr(X, g["states"][it]) < 1e-10
+        assert relerr(Xs, g["states"][it]) < 1e-10
+
+
+@pytest.mark.parametrize("fname", ["lotka_volterra_T50.npz", "lorenz_attractor_T150.npz",
+                                   "protein_transduction_T99.npz"])
+def test_multi_parameter_models_patched(fname):
+    g = load(fname)
+    lin, names = _lin_from_golden(g, [str(s) for s in g["lines"]], [str(s) for s in g["params"]])
+    clamp = bool(g["clamp"])
+    observed = [str(s) for s in g["observed"]]
+    hidden = [u for u in range(len(names)) if (names[u] not in observed)] if clamp else list(range(len(names)))
+    D, A = g["D"], g["A"]
+    X = g["X0"].copy()
+    for it in range(g["thetas"].shape[0]):
+        th, m, Sc, Cth = vo.theta_step(X, lin, D, A)
+        assert relerr(th, g["thetas"][it]) < 1e-9
+        X, _ = vo.state_sweep(X, th, lin, D, hidden)
+        assert relerr(X, g["states"][it]) < 1e-9
+
+
+def test_fit_state_observations():
+    g = load("fitting_state_observations.npz")
+    mean, inv_cov = vo.fit_state_observations(g["Y"], list(g["obs_cols"]), len(g["names"]), float(g["SNR"]),
+                                              g["C"], g["Cobs"], g["Cso"])
+    assert relerr(mean, g["mean"]) < 1e-10
+
+
+def test_state_cov_closed_form_matches_general():
+    g = load("lorenz96_K10_T40.npz")
+    lin, names = _lin_from_golden(g, vo.lorenz96_ode_lines(10), ["_alpha"])
+    D, A, X = g["D"], g["A"], g["X0"]
+    _, covs = vo.state_sweep(X, [8.0], lin, D, [1, 3], A=A, cov_states=(3,))
+    # state 1 is updated before 3 but covariances depend only on the snapshot
+    assert relerr(vo.lorenz96_state_cov(X, 3, D, A), covs[3]) < 1e-12
+
+
+@pytest.mark.skipif(not rs.reference_available(), reason="live reference not present (GPU box)")
+def test_oracle_vs_live_reference_lorenz96():
+    import pandas as pd
+    ref = rs.load_reference()
+    K, T = 10, 60
+    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=5)
+    rng = np.random.default_rng(7)
+    X0 = Xtrue + 0.4 * rng.standard_normal(Xtrue.shape)
+    names = ["_x_%d" % (i + 1) for i in range(K)]
+    state, param = sym.symbols(names), sym.symbols(["_alpha"])
+    symbols = rs.Symbols(state, param)
+    odes, odes_sym = ref.import_odes.import_odes(symbols, os.path.join(rs.REFERENCE_DIR, "Lorenz96_ODEs.txt"))
+    sc, _ = ref.import_odes.find_state_couplings_in_odes(odes_sym, symbols)
+    assert sc == vo.state_couplings(vo.parse_ode_lines(vo.lorenz96_ode_lines(K)), state)
+    Dr, Ar, *_ = ref.GP_regression.kernel_function(t, t, "rbf", [0.0625, 1.0])
+    D, A, *_ = vo.kernel_function(t, t, "rbf", [0.0625, 1.0])
+    assert relerr(D, Dr) < 1e-11 and relerr(A, Ar) < 1e-11
+    lin = rs.LocallyLinearODEs()
+    lin.ode_param.B, lin.ode_param.b = ref.rewrite.rewrite_odes_as_linear_combination_in_parameters(odes, state, param)
+    lin.state.R, lin.state.r = ref.rewrite.rewrite_odes_as_linear_combination_in_states(odes, state, param, state[0::2], sc)
+    obs = pd.DataFrame(X0[:, 0::2], index=t, columns=names[0::2])
+    sp = rs.writable_frame(X0, t, names)
+    th = ref.proxies_strict.proxy_for_ode_parameters(sp, lin, Dr, Ar, param, None, odes, None, None, 'analytical')
+    out = ref.proxies_strict.proxy_for_ind_states(rs.writable_frame(X0, t, names), th, odes, None, lin, Dr, Ar,
+                                                  None, None, obs, None, sc, 5, True, None, 'analytical')
+    assert relerr(vo.lorenz96_theta_step(X0, Dr, Ar)[0], th.values.ravel()[0]) < 1e-13
+    assert relerr(vo.lorenz96_state_sweep(X0, 8.0, Dr, list(range(1, K, 2))), out.values) < 1e-11
