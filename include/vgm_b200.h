@@ -1,0 +1,247 @@
+/* libvgm_b200 -- C ABI of the B200-native variational gradient-matching hot path.
+ *
+ * The reference (ngorbach/Variational_Gradient_Matching_for_Dynamical_Systems) has no FFI:
+ * its boundary is the Python function surface of VGM_modules/.  Each entry point below is
+ * what a Python (ctypes) binding for one reference site calls; the site it replaces is
+ * cited as file:line relative to the reference's VGM_modules/ directory.
+ *
+ * Conventions
+ *   - every function returns VGM_OK (0) or a negative VGM_E* code; vgm_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - pointers are DEVICE pointers unless the name ends in _host; all matrices are FP64,
+ *     row-major; state arrays are [n_states][ld] with one state's trajectory contiguous
+ *     (ld >= T, ld even, base 16-byte aligned);
+ *   - nothing allocates persistent device memory: scratch comes in through explicit
+ *     workspace pointers sized by the matching *_ws_bytes() function;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); only the functions
+ *     documented as synchronising (they return host scalars) wait for the device;
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef VGM_B200_H
+#define VGM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vgm_stream_t; /* cudaStream_t */
+
+enum {
+  VGM_OK = 0,
+  VGM_EINVAL = -1,   /* bad argument (shape, alignment, null pointer)          */
+  VGM_ECUDA = -2,    /* CUDA runtime error                                      */
+  VGM_ENOTCONV = -3, /* iterative solve hit max_iter before reaching tolerance  */
+  VGM_ENOTSPD = -4,  /* Cholesky pivot <= 0                                     */
+  VGM_EDRIVER = -5   /* CUDA driver API / module loading failure                */
+};
+
+const char* vgm_last_error(void);
+int vgm_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * G1  GP_regression.kernel_function, GP_regression.py:160-260
+ * Fused build of C, dC = dk/dt0, ddC = d2k/dt0dt1 on t (T x T, leading dimension ld),
+ * C_obs on t2 (T2 x T2, ld2) and C_state_obs (T x T2, ld2).  Any output pointer may be null.
+ * kernel_type: VGM_KERNEL_RBF  param_host = [lengthscale, sigma]         (GP_regression.py:176-179)
+ *              VGM_KERNEL_RQ   param_host = [alpha, lengthscale, sigma]  (GP_regression.py:205-209)
+ * The result is scaled by sigma^2 = param[-1]^2 (GP_regression.py:232).
+ */
+enum { VGM_KERNEL_RBF = 0, VGM_KERNEL_RQ = 1 };
+int vgm_kernel_build(int kernel_type, const double* param_host, int n_param,
+                     const double* t, int T, const double* t2, int T2, int ld, int ld2,
+                     double* C, double* dC, double* ddC, double* Cobs, double* Cso,
+                     vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense FP64 tensor-core GEMM, C[n][m] = alpha * sum_k A[n][k] B[m][k] + epilogue.
+ * Replaces every np.dot with a T x T operator on the hot path
+ * (proxies_for_ode_parameters_and_states.py:76,225,231,232; GP_regression.py:306,317).
+ * Epilogue: C = alpha*acc + beta*C0 + g1*(U1 ? U1 : 1).V1 + g2*(U2 ? U2 : 1).V2 (elementwise,
+ * operands laid out like C); optional per-row partial dot products
+ * dot_out[row*dot_ld + column_tile] = sum_{m in tile} dotw[row][m] * C[row][m].
+ * rowsA / rowsC (optional) map logical row n to a physical row of A / of C and of every
+ * epilogue operand; n_rows_dev (optional) is a device-side row count (<= N).
+ */
+typedef struct {
+  const double* A;
+  const double* B;
+  double* C;
+  int lda, ldb, ldc;
+  int N, M, K;
+  const int* rowsA;
+  const int* rowsC;
+  const int* n_rows_dev;
+  double alpha, beta;
+  const double* C0;
+  const double* U1;
+  const double* V1;
+  double g1;
+  const double* U2;
+  const double* V2;
+  double g2;
+  const double* dotw;
+  double* dot_out;
+  int dot_ld;
+} vgm_gemm_args;
+int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream);
+int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row of dot_out */
+int vgm_transpose(const double* in, int ld_in, double* out, int ld_out, int rows, int cols, vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * G2  GP_regression.kernel_function, GP_regression.py:306,317
+ *   D = dC C^-1  (reference: LU solve on the transposes), A = ddC - D dC^T.
+ * Cholesky route: C = L L^T, C^-1 = L^-T L^-1, then two DMMA GEMMs.  `batch` hyper-parameter
+ * sets are processed back to back; matrices of set b start at base + b*T*ld.
+ * Also exposes the SPD inverse used for the shared-operator preconditioner.
+ * Returns VGM_ENOTSPD (after a device sync) if a pivot is not positive.
+ */
+size_t vgm_gm_operators_ws_bytes(int T, int ld);
+int vgm_gm_operators(const double* C, const double* dC, const double* ddC, int T, int ld, int batch,
+                     double* D, double* A, double* Cinv, void* ws, size_t ws_bytes, vgm_stream_t stream);
+int vgm_spd_inverse(const double* S, int T, int ld, double* Sinv, void* ws, size_t ws_bytes, vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * G3/G4  rewrite_odes_as_local_linear_combinations.py:28-58,76-124
+ * A "program" holds the model-specific coefficient kernels (B_k, b_k per ODE; R_uk, r_uk per
+ * state x ODE) generated from the SymPy rewrite as CUDA device functions.  Programs are
+ * either compiled ahead of time into this library (Lorenz96) or loaded from a cubin that
+ * the Python code generator produced with NVRTC for sm_100a.
+ */
+typedef struct vgm_program vgm_program;
+int vgm_program_builtin(const char* name, vgm_program** out); /* "lorenz96" */
+int vgm_program_load(const void* cubin_host, size_t size, int n_param, int arity, vgm_program** out);
+int vgm_program_free(vgm_program* prog);
+int vgm_program_n_param(const vgm_program* prog);
+
+/* ------------------------------------------------------------------------------------
+ * P2/P3  proxy_for_ode_parameters, proxies_for_ode_parameters_and_states.py:58-93
+ * Sufficient statistics  m = sum_k B_k^T (D x_k - b_k),  S = sum_k B_k^T B_k  over n_odes
+ * ODE rows.  ODE row j belongs to structural class ode_class[j] and reads the states
+ * ode_idx[j*arity .. j*arity+arity) (rows of X); its own state (row of DX) is ode_state[j].
+ * Output stats = [m (p) | S (p*p, row-major)] on the device (so NCCL can all-reduce it in
+ * place); vgm_param_solve solves S theta = m (constraints=None, proxies...py:93).
+ */
+size_t vgm_param_stats_ws_bytes(int n_odes, int T, int n_param);
+int vgm_param_stats(const vgm_program* prog, const double* X, const double* DX, int ld, int T,
+                    int n_odes, const int* ode_class, const int* ode_idx, const int* ode_state,
+                    double* stats, void* ws, size_t ws_bytes, vgm_stream_t stream);
+int vgm_param_solve(const double* stats, int n_param, double* theta, vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * P4  proxy_for_ind_states (optimizer='analytical'), proxies...py:185-262
+ * The sweep plan (index tables on the device, built once by the host from state_couplings).
+ * Hidden "slot" i is the i-th hidden state in the reference's update order.
+ */
+typedef struct {
+  int T, ld;                 /* time points, leading dimension of every [rows][ld] array     */
+  int n_hidden;              /* K_h                                                          */
+  const int* slot_state;     /* [n_hidden] state index (row of X) of each slot               */
+  const int* pair_ptr;       /* [n_hidden+1] CSR over (slot, coupled ODE) pairs, c(u) order  */
+  const int* pair_ode;       /* [n_pairs] ODE row j (index into ode_idx / ode_state)         */
+  const int* pair_code;      /* [n_pairs] generated-function selector (class, position)      */
+  const int* pair_live;      /* [n_pairs] -1: D.x_k from the sweep-start snapshot; >=0: slot
+                                in the live buffer (state already updated in this sweep,
+                                proxies...py:225 reads the live column)                      */
+  const int* pair_self;      /* [n_pairs] 1 if ODE k == u (proxies...py:228-232)             */
+  const int* ode_idx;        /* [n_odes*arity] gather table (shared with vgm_param_stats)    */
+  const int* ode_state;      /* [n_odes]                                                     */
+  const int* slot_has_self;  /* [n_hidden] 0 => u not in c(u): reference doubles diag (:201,:245) */
+  int n_levels;              /* dependency wavefronts that reproduce the sequential order    */
+  const int* level_ptr_host; /* [n_levels+1] HOST array                                      */
+  const int* level_slots;    /* [n_hidden] slots grouped by level (device)                   */
+  int n_live;                /* states whose updated D.x is read later in the same sweep     */
+  const int* live_state;     /* [n_live] state index of each live slot (device)              */
+  const int* live_level_ptr_host; /* [n_levels+1] HOST: live slots grouped by producing level */
+  int n_live_pairs;          /* pairs with pair_live >= 0                                    */
+  const int* live_pair_slot; /* [n_live_pairs] hidden slot of each live pair, grouped by the level of the slot */
+  const int* live_pair_src;  /* [n_live_pairs] live-buffer slot it reads                     */
+  const int* live_pair_level_ptr_host; /* [n_levels+1] HOST                                  */
+  int ruu_const;             /* 1 => R_uu is the same constant for every hidden state        */
+  double ruu_value;          /*      that constant (Lorenz96: -1)                            */
+} vgm_sweep_plan;
+
+typedef struct {
+  const double* D;   /* dC C^-1, T x ld                                 */
+  const double* DT;  /* its transpose                                   */
+  const double* M;   /* (c I - D)^T (c I - D) if plan.ruu_const else null */
+  const double* G;   /* optional preconditioner (M + shift I)^-1, else null */
+} vgm_operators;
+
+typedef struct {
+  double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)  */
+  int max_iter;      /* default 4 T                                                        */
+  int check_every;   /* host polls the device-side active count every this many iterations */
+} vgm_solver_opts;
+
+typedef struct {
+  int iterations;    /* CG iterations executed (max over states)    */
+  int unconverged;   /* states that hit max_iter                    */
+  int gemm_calls;    /* DGEMM launches inside the sweep             */
+  int kernel_launches;
+} vgm_sweep_info;
+
+size_t vgm_state_sweep_ws_bytes(const vgm_sweep_plan* plan);
+/* X is updated in place (hidden rows only).  DX0 must hold D.x_k of the sweep-start X for every
+ * state (it is what vgm_param_stats consumed).  theta_star: device pointer to the p parameter
+ * values plugged into R_uk, r_uk (the reference hard-codes [8], proxies...py:211).
+ * Synchronises the stream (convergence polling). */
+int vgm_state_sweep(const vgm_program* prog, const vgm_sweep_plan* plan, const vgm_operators* ops,
+                    const vgm_solver_opts* opts, double* X, const double* DX0, const double* theta_star,
+                    void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
+
+/* One building block of the sweep, exposed for tests: snapshot coefficients
+ * Lambda_u = sum_{k!=u} R_uk^2, rhs_u (without the -B_uu^T r_uu term and without live terms),
+ * r_uu, R_uu and the R_uk of live pairs (all [n_hidden or n_live_pairs][ld]). */
+int vgm_state_assemble(const vgm_program* prog, const vgm_sweep_plan* plan, const double* X, const double* DX0,
+                       const double* theta_star, double* Lambda, double* rhs, double* ruu, double* Ruu,
+                       double* Rlive, vgm_stream_t stream);
+
+/* Batched (preconditioned) conjugate gradients on rows:  (Op + diag(Lambda_i)) x_i = rhs_i with
+ * Op = M (shared, one GEMM per iteration) or Op_i = (diag(Ruu_i) - D)^T (diag(Ruu_i) - D)
+ * (matrix-free, two GEMMs).  Ruu / Lambda / rhs are [n_hidden][ld] indexed by hidden slot;
+ * rows[] lists the n_rows slots to solve; x lives in X rows slot_state[slot] and its current
+ * content is the initial guess.  Synchronises the stream. */
+size_t vgm_pcg_ws_bytes(int n_hidden, int T, int ld);
+int vgm_pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu, const double* Lambda, const double* rhs,
+                  double* X, const int* slot_state, int n_hidden, const int* rows, int n_rows, int T, int ld,
+                  const vgm_solver_opts* opts, void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * P5  state "covariance" proxies...py:190,239 (opt-in; the reference computes and drops it)
+ *   Cov_u = sum_{k in c(u)} B_uk^T A B_uk  for one hidden slot, T x ld output.
+ */
+size_t vgm_state_cov_ws_bytes(int T, int ld);
+int vgm_state_cov(const vgm_program* prog, const vgm_sweep_plan* plan, const vgm_operators* ops, const double* A,
+                  const double* X, const double* theta_star, int slot, double* cov, void* ws, size_t ws_bytes,
+                  vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole coordinate-ascent iteration with HOST buffers (the end-to-end path):
+ *   H2D X -> D.X GEMM -> theta statistics + solve -> state sweep -> D2H X, theta.
+ * X_host is [n_states][ld] pinned or pageable host memory, updated in place.
+ */
+typedef struct {
+  int n_states, n_odes, n_param;
+  const int* ode_class;
+  const int* ode_idx;
+  const int* ode_state;
+  int theta_mode; /* 0: plug theta_literal into R,r (reference, proxies...py:211); 1: plug the fresh theta */
+  double theta_literal[8];
+} vgm_model_tables;
+size_t vgm_iteration_ws_bytes(const vgm_model_tables* model, const vgm_sweep_plan* plan);
+int vgm_iteration_device(const vgm_program* prog, const vgm_model_tables* model, const vgm_sweep_plan* plan,
+                         const vgm_operators* ops, const vgm_solver_opts* opts, double* X, double* DX,
+                         double* theta, double* stats, void* ws, size_t ws_bytes, vgm_sweep_info* info,
+                         vgm_stream_t stream);
+int vgm_iteration_host(const vgm_program* prog, const vgm_model_tables* model, const vgm_sweep_plan* plan,
+                       const vgm_operators* ops, const vgm_solver_opts* opts, double* X_host, double* theta_host,
+                       double* X_dev, double* DX_dev, double* theta_dev, double* stats_dev,
+                       void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGM_B200_H */

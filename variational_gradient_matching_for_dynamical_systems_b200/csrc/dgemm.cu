@@ -1,0 +1,248 @@
+// FP64 tensor-core GEMM for the gradient-matching operators (sm_100a, DMMA mma.sync m16n8k8).
+//
+//   C[n][m] = alpha * sum_k A[n][k] * B[m][k]  (+ beta*C0 + g1*U1.V1 + g2*U2.V2)   "NT": both operands K-contiguous
+//
+// This one form covers every dense contraction on the reference hot path because a state's
+// trajectory is contiguous in HBM (X is [K_states][T]):
+//   D.x_k for all k      proxies_for_ode_parameters_and_states.py:76,225   A = X,      B = D
+//   (diag(R)-D)^T r      proxies...py:231                                  A = r_uu,   B = D^T
+//   B^T B p  (CG)        proxies...py:232,262 (solve)                      A = P,      B = M or D, D^T
+//   dC C^-1, D dC^T      GP_regression.py:306,317                          A = dC / D, B = C^-1 / dC
+//
+// tcgen05 has no f64 kind, so FP64 tensor work on sm_100a is warp-level DMMA.  The B operand
+// (a T x T operator, 8 MB at T=1000) stays L2 resident; the A operand streams from HBM once
+// per column-tile sweep.  Operands are staged through a 4-deep cp.async ring in shared
+// memory with a +4 double row pad (conflict-free 64-bit fragment loads).
+#include "vgm_common.cuh"
+
+namespace vgm {
+
+template <int BM_, int BN_, int WARPS_M_, int WARPS_N_>
+struct GemmCfg {
+  static constexpr int BM = BM_, BN = BN_, BK = 16, LDS = BK + 4, STAGES = 4;
+  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
+  static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
+  static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
+  static constexpr int MT = WM / 16, NT = WN / 8;             // mma tiles per warp
+  static constexpr int SMEM = STAGES * (BM + BN) * LDS * (int)sizeof(double);
+  static_assert(WM % 16 == 0 && WN % 8 == 0, "warp tile must be a multiple of the MMA tile");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) dgemm_nt_kernel(const vgm_gemm_args a) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, STAGES = Cfg::STAGES;
+  constexpr int MT = Cfg::MT, NT = Cfg::NT, THREADS = Cfg::THREADS;
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;                        // [STAGES][BM][LDS]
+  double* Bs = smem + STAGES * BM * LDS;    // [STAGES][BN][LDS]
+
+  const int N = a.n_rows_dev ? min(*a.n_rows_dev, a.N) : a.N;
+  const int n0 = blockIdx.y * BM;
+  if (n0 >= N) return;
+  const int m0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- global -> shared copy plan: 16-byte chunks, BK/2 per tile row --------------
+  constexpr int CPR = BK / 2;                       // chunks per row
+  constexpr int A_CHUNKS = BM * CPR / THREADS;      // per thread
+  constexpr int B_CHUNKS = BN * CPR / THREADS;
+  static_assert((BM * CPR) % THREADS == 0 && (BN * CPR) % THREADS == 0, "tile/threads mismatch");
+  const double* a_src[A_CHUNKS];
+  const double* b_src[B_CHUNKS];
+  int a_dst[A_CHUNKS], b_dst[B_CHUNKS];
+#pragma unroll
+  for (int i = 0; i < A_CHUNKS; ++i) {
+    const int id = tid + i * THREADS, r = id / CPR, c = id % CPR;
+    int n = min(n0 + r, N - 1);
+    if (a.rowsA) n = a.rowsA[n];
+    a_src[i] = a.A + (size_t)n * a.lda + 2 * c;
+    a_dst[i] = r * LDS + 2 * c;
+  }
+#pragma unroll
+  for (int i = 0; i < B_CHUNKS; ++i) {
+    const int id = tid + i * THREADS, r = id / CPR, c = id % CPR;
+    const int m = min(m0 + r, a.M - 1);
+    b_src[i] = a.B + (size_t)m * a.ldb + 2 * c;
+    b_dst[i] = r * LDS + 2 * c;
+  }
+  const int kc_of_thread = 2 * (tid % CPR);         // same column offset for every chunk of this thread
+  const int KT = (a.K + BK - 1) / BK;
+
+  auto load_stage = [&](int kt) {
+    const int st = kt % STAGES;
+    const int k0 = kt * BK;
+    int bytes = (a.K - (k0 + kc_of_thread)) * 8;
+    bytes = max(0, min(16, bytes));
+    const int koff = (bytes > 0) ? k0 : 0;          // keep the address in bounds when fully masked
+    double* as = As + st * BM * LDS;
+    double* bs = Bs + st * BN * LDS;
+#pragma unroll
+    for (int i = 0; i < A_CHUNKS; ++i) cp_async16(as + a_dst[i], a_src[i] + koff, bytes);
+#pragma unroll
+    for (int i = 0; i < B_CHUNKS; ++i) cp_async16(bs + b_dst[i], b_src[i] + koff, bytes);
+  };
+
+  double acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_stage(s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {  // prefetch tile kt+STAGES-1 into the slot freed by iteration kt-1
+      const int nk = kt + STAGES - 1;
+      if (nk < KT) load_stage(nk);
+      cp_async_commit();
+    }
+    const double* as = As + (kt % STAGES) * BM * LDS + (wm * Cfg::WM) * LDS;
+    const double* bs = Bs + (kt % STAGES) * BN * LDS + (wn * Cfg::WN) * LDS;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 8) {
+      double af[MT][4], bf[NT][2];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const double* p = as + (i * 16 + g) * LDS + kk + t;
+        af[i][0] = p[0];
+        af[i][1] = p[8 * LDS];
+        af[i][2] = p[4];
+        af[i][3] = p[8 * LDS + 4];
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double* p = bs + (j * 8 + g) * LDS + kk + t;
+        bf[j][0] = p[0];
+        bf[j][1] = p[4];
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma_16x8x8(acc[i][j], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue ---------------------------------------------------------------------
+  // thread owns rows {g, g+8} of each 16-row tile and column pairs (2t, 2t+1) of each 8-col tile
+  const bool want_dot = (a.dot_out != nullptr);
+  __shared__ double dot_sm[Cfg::WARPS_N][BM];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rl = wm * Cfg::WM + i * 16 + g + 8 * h;   // row within the CTA tile
+      const int n = n0 + rl;
+      const bool row_ok = n < N;
+      int nc = row_ok ? n : N - 1;
+      if (a.rowsC) nc = a.rowsC[nc];
+      const size_t roff = (size_t)nc * a.ldc;
+      double dsum = 0.0;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int m = m0 + wn * Cfg::WN + j * 8 + 2 * t;
+        if (row_ok && m < a.M) {
+          const bool two = (m + 1 < a.M);
+          double v0 = a.alpha * acc[i][j][2 * h], v1 = a.alpha * acc[i][j][2 * h + 1];
+          const size_t o = roff + m;
+          if (a.C0) {
+            v0 += a.beta * a.C0[o];
+            if (two) v1 += a.beta * a.C0[o + 1];
+          }
+          if (a.V1) {
+            v0 += a.g1 * (a.U1 ? a.U1[o] : 1.0) * a.V1[o];
+            if (two) v1 += a.g1 * (a.U1 ? a.U1[o + 1] : 1.0) * a.V1[o + 1];
+          }
+          if (a.V2) {
+            v0 += a.g2 * (a.U2 ? a.U2[o] : 1.0) * a.V2[o];
+            if (two) v1 += a.g2 * (a.U2 ? a.U2[o + 1] : 1.0) * a.V2[o + 1];
+          }
+          if (two) {
+            *reinterpret_cast<double2*>(a.C + o) = make_double2(v0, v1);
+          } else {
+            a.C[o] = v0;
+          }
+          if (want_dot) {
+            dsum += a.dotw[o] * v0;
+            if (two) dsum += a.dotw[o + 1] * v1;
+          }
+        }
+      }
+      if (want_dot) {
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+        if (t == 0) dot_sm[wn][rl] = dsum;
+      }
+    }
+  }
+  if (want_dot) {
+    __syncthreads();
+    for (int r = tid; r < BM; r += THREADS) {
+      const int n = n0 + r;
+      if (n < N) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS_N; ++w) s += dot_sm[w][r];
+        const int nc = a.rowsC ? a.rowsC[n] : n;
+        a.dot_out[(size_t)nc * a.dot_ld + blockIdx.x] = s;
+      }
+    }
+  }
+}
+
+template <class Cfg>
+static int launch_gemm(const vgm_gemm_args& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VGM_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(a.M, Cfg::BN), ceil_div(a.N, Cfg::BM));
+  dgemm_nt_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+using CfgBig = GemmCfg<128, 128, 2, 4>;   // 256 threads, warp tile 64x32
+using CfgMid = GemmCfg<64, 64, 2, 2>;     // 128 threads, warp tile 32x32
+using CfgThin = GemmCfg<16, 64, 1, 4>;    // 128 threads, warp tile 16x16 (few rows: halo / tail solves)
+
+int gemm_dot_tiles(int M, int N) {
+  // number of column tiles (= partial dot products per row) the chosen configuration produces
+  if (N <= 16) return ceil_div(M, CfgThin::BN);
+  if ((long long)ceil_div(N, 128) * ceil_div(M, 128) < 120) return ceil_div(M, CfgMid::BN);
+  return ceil_div(M, CfgBig::BN);
+}
+
+int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s) {
+  VGM_REQUIRE(a.A && a.B && a.C, "null operand");
+  VGM_REQUIRE(a.N >= 0 && a.M > 0 && a.K > 0, "bad shape");
+  VGM_REQUIRE((a.lda % 2) == 0 && (a.ldb % 2) == 0 && (a.ldc % 2) == 0, "leading dimensions must be even (16-byte rows)");
+  VGM_REQUIRE(((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.B % 16) == 0 && ((uintptr_t)a.C % 16) == 0, "operands must be 16-byte aligned");
+  if (a.N == 0) return VGM_OK;
+  if (a.N <= 16) return launch_gemm<CfgThin>(a, s);
+  if ((long long)ceil_div(a.N, 128) * ceil_div(a.M, 128) < 120) return launch_gemm<CfgMid>(a, s);
+  return launch_gemm<CfgBig>(a, s);
+}
+
+}  // namespace vgm
+
+extern "C" int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream) {
+  if (!args) {
+    vgm::set_error("vgm_dgemm_nt: null args");
+    return VGM_EINVAL;
+  }
+  return vgm::dgemm_nt(*args, (cudaStream_t)stream);
+}
+
+extern "C" int vgm_dgemm_dot_tiles(int M, int N) { return vgm::gemm_dot_tiles(M, N); }

@@ -1,0 +1,335 @@
+"""Device-resident VGM engine: keeps the state proxies, the gradient-matching operators and
+all index tables in HBM across coordinate-ascent iterations and drives the C ABI
+(``include/vgm_b200.h``).  PyTorch is used only for device memory and streams.
+
+Layout: the state proxy means are stored state-major, ``X[k, t]`` (``[K, ld]``, ``ld`` =
+T rounded up to a multiple of 8), so one state's trajectory is contiguous -- the transpose of
+the reference's ``T x K`` DataFrame (proxies_for_ode_parameters_and_states.py:53,168).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .codegen import OdeModel, Program, build_host_plan
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _i32(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
+
+
+def _host_i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    arr = (C.c_int * max(1, a.size))(*a.tolist())
+    return arr
+
+
+class Operators:
+    """D = dC C^-1 (T x T) and friends on the device, padded to leading dimension ld."""
+
+    def __init__(self, D, A=None, ld=None, device=None):
+        self.dev = device or _lib.require_cuda()
+        D = np.asarray(D, dtype=np.float64) if not torch.is_tensor(D) else D
+        T = D.shape[0]
+        if D.shape[0] != D.shape[1]:
+            raise ValueError("dC_times_invC is not a square matrix")
+        self.T = T
+        self.ld = ld or _round_up(T, 8)
+        self.D = self._pad(D)
+        self.DT = self._pad(self.D[:, :T].t().contiguous())
+        self.A = self._pad(A) if A is not None else None
+        self.M = None
+        self.M_c = None
+        self.G = None
+        self.G_shift = None
+
+    def _pad(self, M):
+        out = torch.zeros((self.T, self.ld), dtype=torch.float64, device=self.dev)
+        out[:, :self.T] = torch.as_tensor(M, dtype=torch.float64, device=self.dev)[:, :self.T]
+        return out
+
+    def ensure_shared_M(self, c):
+        """M = (c I - D)^T (c I - D): the shared system matrix when R_uu == c for every state
+        (proxies...py:229,232 with R = c I)."""
+        if self.M is not None and self.M_c == c:
+            return self.M
+        lib = _lib.load()
+        T, ld = self.T, self.ld
+        BT = -self.DT.clone()                      # (c I - D)^T = c I - D^T, rows K-contiguous
+        BT[:, :T] += c * torch.eye(T, dtype=torch.float64, device=self.dev)
+        M = torch.zeros_like(BT)
+        g = _lib.GemmArgs()
+        g.A, g.B, g.C = BT.data_ptr(), BT.data_ptr(), M.data_ptr()
+        g.lda = g.ldb = g.ldc = ld
+        g.N = g.M = g.K = T
+        g.alpha = 1.0
+        _lib.check(lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
+        self.M, self.M_c = M, c
+        self.G = None
+        return M
+
+    def ensure_preconditioner(self, shift):
+        """G = (M + shift I)^-1 by Cholesky on the device (vgm_spd_inverse)."""
+        if self.G is not None and self.G_shift is not None and 0.5 * self.G_shift <= shift <= 2.0 * self.G_shift:
+            return self.G
+        lib = _lib.load()
+        T, ld = self.T, self.ld
+        S = self.M.clone()
+        S[:, :T] += shift * torch.eye(T, dtype=torch.float64, device=self.dev)
+        G = torch.zeros_like(S)
+        nbytes = lib.vgm_gm_operators_ws_bytes(T, ld)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        _lib.check(lib.vgm_spd_inverse(S.data_ptr(), T, ld, G.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr()))
+        self.G, self.G_shift = G, float(shift)
+        return G
+
+
+class DevicePlan:
+    """``vgm_sweep_plan`` with its device/host arrays kept alive."""
+
+    def __init__(self, model: OdeModel, hidden, T, ld, tables, couplings=None, schedule="reference", device=None):
+        dev = device or _lib.require_cuda()
+        hp = build_host_plan(model, hidden, couplings=couplings, schedule=schedule)
+        self.host = hp
+        keep = self._keep = {}
+        for name in ("slot_state", "pair_ptr", "pair_ode", "pair_code", "pair_live", "pair_self", "slot_has_self",
+                     "level_slots", "live_state", "live_pair_slot", "live_pair_src"):
+            arr = getattr(hp, name)
+            keep[name] = _i32(arr if len(arr) else np.zeros(1, dtype=np.int32), dev)
+        for name in ("level_ptr", "live_level_ptr", "live_pair_level_ptr"):
+            keep[name + "_host"] = _host_i32(getattr(hp, name))
+        p = _lib.SweepPlan()
+        p.T, p.ld, p.n_hidden = T, ld, hp.n_hidden
+        p.slot_state = keep["slot_state"].data_ptr()
+        p.pair_ptr = keep["pair_ptr"].data_ptr()
+        p.pair_ode = keep["pair_ode"].data_ptr()
+        p.pair_code = keep["pair_code"].data_ptr()
+        p.pair_live = keep["pair_live"].data_ptr()
+        p.pair_self = keep["pair_self"].data_ptr()
+        p.ode_idx = tables["ode_idx"].data_ptr()
+        p.ode_state = tables["ode_state"].data_ptr()
+        p.slot_has_self = keep["slot_has_self"].data_ptr()
+        p.n_levels = hp.n_levels
+        p.level_ptr_host = C.cast(keep["level_ptr_host"], C.POINTER(C.c_int))
+        p.level_slots = keep["level_slots"].data_ptr()
+        p.n_live = hp.n_live
+        p.live_state = keep["live_state"].data_ptr()
+        p.live_level_ptr_host = C.cast(keep["live_level_ptr_host"], C.POINTER(C.c_int))
+        p.n_live_pairs = hp.n_live_pairs
+        p.live_pair_slot = keep["live_pair_slot"].data_ptr()
+        p.live_pair_src = keep["live_pair_src"].data_ptr()
+        p.live_pair_level_ptr_host = C.cast(keep["live_pair_level_ptr_host"], C.POINTER(C.c_int))
+        p.ruu_const, p.ruu_value = hp.ruu_const, hp.ruu_value
+        self.c = p
+        self.n_hidden = hp.n_hidden
+        self.hidden = np.asarray(hp.slot_state, dtype=np.int64)
+
+
+class VGMEngine:
+    """Mean-field variational gradient matching on one GPU.
+
+    Parameters
+    ----------
+    model : OdeModel
+    D, A : T x T operators ``dC_times_inv_C`` and ``eps_cov`` (GP_regression.py:306,317)
+    hidden : state indices to update, in the reference's order (proxies...py:175-179,195)
+    theta_mode : 'reference' plugs the literal ``theta_literal`` (default [8.0], the value
+        hard-coded at proxies...py:211) into R_uk, r_uk; 'proxy' plugs the current estimate.
+    """
+
+    def __init__(self, model: OdeModel, D, A=None, hidden=None, couplings=None, schedule="reference",
+                 theta_mode="reference", theta_literal=(8.0,), tol=1e-13, max_iter=0, check_every=8,
+                 precondition=True, prefer_builtin=True, device=None):
+        self.lib = _lib.load()
+        self.dev = device or _lib.require_cuda()
+        self.model = model
+        self.ops = D if isinstance(D, Operators) else Operators(D, A, device=self.dev)
+        self.T, self.ld = self.ops.T, self.ops.ld
+        self.K, self.p = model.K, model.p
+        self.program = Program(model, prefer_builtin=prefer_builtin)
+        self.tables = {"ode_class": _i32(model.ode_class, self.dev), "ode_idx": _i32(model.ode_idx, self.dev),
+                       "ode_state": _i32(model.ode_state, self.dev)}
+        if hidden is None:
+            hidden = np.arange(self.K)
+        self.plan = DevicePlan(model, hidden, self.T, self.ld, self.tables, couplings=couplings, schedule=schedule,
+                               device=self.dev)
+        if theta_mode not in ("reference", "proxy"):
+            raise ValueError("theta_mode must be 'reference' or 'proxy'")
+        self.theta_mode = theta_mode
+        self.theta_literal = tuple(float(v) for v in theta_literal)
+        if theta_mode == "reference" and len(self.theta_literal) != self.p:
+            raise TypeError("the reference plugs the literal [8] into R_uk, r_uk (proxies...py:211); a model with %d "
+                            "parameters needs theta_mode='proxy' or a theta_literal of that length" % self.p)
+        self.precondition = bool(precondition)
+        self.opts = _lib.SolverOpts(tol, max_iter, check_every)
+        self.X = torch.zeros((self.K, self.ld), dtype=torch.float64, device=self.dev)
+        self.DX = torch.zeros_like(self.X)
+        self.theta = torch.zeros(max(self.p, 1), dtype=torch.float64, device=self.dev)
+        self.theta_star = torch.zeros(max(self.p, 1), dtype=torch.float64, device=self.dev)
+        self.stats = torch.zeros(self.p + self.p * self.p, dtype=torch.float64, device=self.dev)
+        self._cops = _lib.Operators()
+        self._cops.D, self._cops.DT = self.ops.D.data_ptr(), self.ops.DT.data_ptr()
+        if self.plan.c.ruu_const:
+            self._cops.M = self.ops.ensure_shared_M(self.plan.c.ruu_value).data_ptr()
+        self._mt = _lib.ModelTables()
+        self._mt.n_states, self._mt.n_odes, self._mt.n_param = self.K, self.K, self.p
+        self._mt.ode_class = self.tables["ode_class"].data_ptr()
+        self._mt.ode_idx = self.tables["ode_idx"].data_ptr()
+        self._mt.ode_state = self.tables["ode_state"].data_ptr()
+        self._mt.theta_mode = 0 if theta_mode == "reference" else 1
+        for i, v in enumerate(self.theta_literal[:8]):
+            self._mt.theta_literal[i] = v
+        n_ws = max(self.lib.vgm_iteration_ws_bytes(C.byref(self._mt), C.byref(self.plan.c)), 1024)
+        self.ws = torch.empty(n_ws, dtype=torch.uint8, device=self.dev)
+        self.info = _lib.SweepInfo()
+        self.last_info = None
+
+    # ---- data movement ---------------------------------------------------------------------
+    def set_states(self, X_TK):
+        """Upload a T x K array (reference orientation)."""
+        X = torch.as_tensor(np.asarray(X_TK, dtype=np.float64)) if not torch.is_tensor(X_TK) else X_TK
+        if X.shape != (self.T, self.K):
+            raise ValueError("Either state_proxy or dC_times_invC have the wrong shape")
+        self.X.zero_()
+        self.X[:, :self.T] = X.to(self.dev, dtype=torch.float64).t()
+        return self
+
+    def set_states_state_major(self, X_KT):
+        self.X.zero_()
+        self.X[:, :self.T] = torch.as_tensor(X_KT, dtype=torch.float64, device=self.dev)[:, :self.T]
+        return self
+
+    def get_states(self):
+        """T x K numpy array (reference orientation)."""
+        return self.X[:, :self.T].t().contiguous().cpu().numpy()
+
+    def get_theta(self):
+        return self.theta[:self.p].cpu().numpy()
+
+    # ---- preconditioner -----------------------------------------------------------------------
+    def _prepare_preconditioner(self):
+        if not (self.precondition and self.plan.c.ruu_const) or self.plan.n_hidden == 0:
+            self._cops.G = None
+            return
+        if self.ops.G is None:
+            # shift = mean of Lambda over all hidden states/time points of the current proxy
+            nh, ld = self.plan.n_hidden, self.ld
+            lam = torch.empty((nh, ld), dtype=torch.float64, device=self.dev)
+            tmp = [torch.empty_like(lam) for _ in range(2)]
+            nlp = max(self.plan.c.n_live_pairs, 1)
+            rlive = torch.empty((nlp, ld), dtype=torch.float64, device=self.dev)
+            self._set_theta_star()
+            _lib.check(self.lib.vgm_state_assemble(self.program.handle, C.byref(self.plan.c), self.X.data_ptr(),
+                                                   self.DX.data_ptr(), self.theta_star.data_ptr(), lam.data_ptr(),
+                                                   tmp[0].data_ptr(), tmp[1].data_ptr(), None, rlive.data_ptr(),
+                                                   _lib.stream_ptr()))
+            shift = float(lam[:, :self.T].mean().item())
+            if not np.isfinite(shift) or shift <= 0:
+                shift = 1.0
+            self.ops.ensure_preconditioner(shift)
+        self._cops.G = self.ops.G.data_ptr()
+
+    def _set_theta_star(self, theta_star=None):
+        if theta_star is not None:
+            self.theta_star[:self.p] = torch.as_tensor(np.asarray(theta_star, dtype=np.float64).ravel(), device=self.dev)
+        elif self.theta_mode == "reference":
+            self.theta_star[:self.p] = torch.tensor(self.theta_literal, dtype=torch.float64, device=self.dev)
+        else:
+            self.theta_star[:self.p] = self.theta[:self.p]
+
+    # ---- the three building blocks --------------------------------------------------------------
+    def compute_DX(self):
+        """DX[k, :] = D @ x_k for every state (one DMMA GEMM)."""
+        g = _lib.GemmArgs()
+        g.A, g.B, g.C = self.X.data_ptr(), self.ops.D.data_ptr(), self.DX.data_ptr()
+        g.lda = g.ldb = g.ldc = self.ld
+        g.N, g.M, g.K = self.K, self.T, self.T
+        g.alpha = 1.0
+        _lib.check(self.lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
+
+    def param_stats(self):
+        """Sufficient statistics [m | S] of the theta update on the device."""
+        n = self.lib.vgm_param_stats_ws_bytes(self.K, self.T, self.p)
+        _lib.check(self.lib.vgm_param_stats(self.program.handle, self.X.data_ptr(), self.DX.data_ptr(), self.ld, self.T,
+                                            self.K, self._mt.ode_class, self._mt.ode_idx, self._mt.ode_state,
+                                            self.stats.data_ptr(), self.ws.data_ptr(), n, _lib.stream_ptr()))
+        return self.stats
+
+    def param_solve(self):
+        _lib.check(self.lib.vgm_param_solve(self.stats.data_ptr(), self.p, self.theta.data_ptr(), _lib.stream_ptr()))
+        return self.theta
+
+    def theta_step(self):
+        """proxy_for_ode_parameters(optimizer='analytical', constraints=None)."""
+        self.compute_DX()
+        self.param_stats()
+        self.param_solve()
+        return self.theta[:self.p]
+
+    def state_sweep(self, theta_star=None, dx_is_current=True, allow_unconverged=False):
+        """proxy_for_ind_states(optimizer='analytical', constraints=None): one sweep."""
+        if not dx_is_current:
+            self.compute_DX()
+        self._set_theta_star(theta_star)
+        self._prepare_preconditioner()
+        n = self.lib.vgm_state_sweep_ws_bytes(C.byref(self.plan.c))
+        rc = self.lib.vgm_state_sweep(self.program.handle, C.byref(self.plan.c), C.byref(self._cops),
+                                      C.byref(self.opts), self.X.data_ptr(), self.DX.data_ptr(),
+                                      self.theta_star.data_ptr(), self.ws.data_ptr(), n, C.byref(self.info),
+                                      _lib.stream_ptr())
+        self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
+        _lib.check(rc, allow_notconv=allow_unconverged)
+        return self.last_info
+
+    def iteration(self, allow_unconverged=False):
+        """theta update followed by the state sweep, all on the device (vgm_iteration_device)."""
+        if self._cops.G is None and self.precondition and self.plan.c.ruu_const and self.plan.n_hidden:
+            self.compute_DX()
+            self._prepare_preconditioner()
+        rc = self.lib.vgm_iteration_device(self.program.handle, C.byref(self._mt), C.byref(self.plan.c),
+                                           C.byref(self._cops), C.byref(self.opts), self.X.data_ptr(),
+                                           self.DX.data_ptr(), self.theta.data_ptr(), self.stats.data_ptr(),
+                                           self.ws.data_ptr(), self.ws.numel(), C.byref(self.info), _lib.stream_ptr())
+        self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
+        _lib.check(rc, allow_notconv=allow_unconverged)
+        return self.last_info
+
+    def iteration_host(self, X_host_KT: torch.Tensor, theta_host: torch.Tensor, allow_unconverged=False):
+        """End-to-end iteration with HOST buffers (vgm_iteration_host): ``X_host_KT`` is a
+        (pinned) CPU tensor [K, ld], updated in place; ``theta_host`` a CPU tensor [p]."""
+        if self._cops.G is None and self.precondition and self.plan.c.ruu_const and self.plan.n_hidden:
+            self.X.copy_(X_host_KT, non_blocking=True)
+            self.compute_DX()
+            self._prepare_preconditioner()
+        rc = self.lib.vgm_iteration_host(self.program.handle, C.byref(self._mt), C.byref(self.plan.c),
+                                         C.byref(self._cops), C.byref(self.opts), X_host_KT.data_ptr(),
+                                         theta_host.data_ptr(), self.X.data_ptr(), self.DX.data_ptr(),
+                                         self.theta.data_ptr(), self.stats.data_ptr(), self.ws.data_ptr(),
+                                         self.ws.numel(), C.byref(self.info), _lib.stream_ptr())
+        self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
+        _lib.check(rc, allow_notconv=allow_unconverged)
+        return self.last_info
+
+    # ---- opt-in covariance (P5) -------------------------------------------------------------------
+    def state_cov(self, state_index, theta_star=None):
+        """T x T matrix sum_k B_uk^T A B_uk of one hidden state (proxies...py:239)."""
+        if self.ops.A is None:
+            raise ValueError("eps_cov (A) was not given")
+        slots = np.nonzero(self.plan.hidden == int(state_index))[0]
+        if len(slots) == 0:
+            raise ValueError("state %r is not a hidden state of this plan" % (state_index,))
+        self._set_theta_star(theta_star)
+        cov = torch.zeros((self.T, self.ld), dtype=torch.float64, device=self.dev)
+        n = self.lib.vgm_state_cov_ws_bytes(self.T, self.ld)
+        ws = torch.empty(n + 256, dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.vgm_state_cov(self.program.handle, C.byref(self.plan.c), C.byref(self._cops),
+                                          self.ops.A.data_ptr(), self.X.data_ptr(), self.theta_star.data_ptr(),
+                                          int(slots[0]), cov.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr()))
+        return cov[:, :self.T].cpu().numpy()
