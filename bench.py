@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the VGM coordinate-ascent loop (BASELINE.json metric:
+"VGM coordinate-ascent state-time updates/sec (Lorenz96 K=100k, T=1000)").
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's algorithm
+
+A *step* is one full coordinate-ascent iteration -- the ODE-parameter update
+(proxy_for_ode_parameters, optimizer='analytical') followed by the sweep over all hidden states
+(proxy_for_ind_states, optimizer='analytical') -- on synthetic Lorenz96 data of the named shape,
+every step starting from the same initial state proxies (so every step does the same,
+cold-start, amount of work).  value = K_hidden * T * steps / seconds, whole job.
+N > 1 shards the K states into contiguous blocks (strong scaling, NCCL halo exchange + all-reduce).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "VGM coordinate-ascent state-time updates/sec (Lorenz96 K=100k, T=1000)"
+UNIT = "state-time updates/s"
+KERNEL = {"type": "rbf", "param": [0.0625, 1.0]}      # l = 1.25*dt: cond(C) ~ 1e3
+DT = 0.05
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--K", type=int, default=100000)
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--cpu-sample-K", type=int, default=384, help="states in the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-precondition", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm (the Python reference itself cannot
+# travel to the GPU box; oracle/vgm_oracle.py is pinned against it by tests/golden)
+# ----------------------------------------------------------------------------------------------
+def cpu_port_run(K_sample, T, steps, warmup):
+    from oracle import vgm_oracle as vo
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [{k: d.get(k) for k in ("internal_api", "num_threads", "version")} for d in threadpool_info()]
+    except Exception:  # noqa: BLE001
+        blas = None
+    t, X = vo.lorenz96_trajectory(K_sample, T, DT, seed=0)
+    rng = np.random.default_rng(1)
+    X0 = X.copy()
+    X0[:, 1::2] += 0.5 * rng.standard_normal((T, K_sample // 2))
+    D, A, *_ = vo.kernel_function(t, t, KERNEL["type"], KERNEL["param"])
+    hidden = list(range(1, K_sample, 2))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        vo.lorenz96_theta_step(X0, D)
+        vo.lorenz96_state_sweep(X0, 8.0, D, hidden)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = len(hidden) * T * len(times) / total
+    return value, total, blas
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count()
+    steps, warmup = max(1, args.steps), min(args.warmup, 1)
+    Ks = args.cpu_sample_K
+    value, total, blas = cpu_port_run(Ks, args.T, steps, warmup)
+    sample = ("Lorenz96 K=%d (%d hidden), T=%d: %d iteration(s) of the oracle port of the reference's analytical "
+              "theta update + state sweep (dense LAPACK solve per hidden state); per-state cost is flat in K "
+              "(BASELINE.md section 3)" % (Ks, Ks // 2, args.T, steps))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Lorenz96 K=%d T=%d, bounded CPU sample K=%d" % (args.K, args.T, Ks),
+                       "kernel": KERNEL, "dt": DT},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "blas": blas},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    f = [x.strip() for x in ln.split(",")]
+                    if len(f) >= 9:
+                        self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=6)
+        sm = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def native_arm(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from variational_gradient_matching_for_dynamical_systems_b200 import OdeModel, _lib
+    from variational_gradient_matching_for_dynamical_systems_b200.GP_regression import kernel_function_device
+    from variational_gradient_matching_for_dynamical_systems_b200.engine import Operators, VGMEngine
+    from variational_gradient_matching_for_dynamical_systems_b200.synthetic import lorenz96_problem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    K, T = args.K, args.T
+
+    # ---- one-time set-up (excluded from the metric, reported separately) ------------------------
+    t_setup0 = time.perf_counter()
+    tgrid = np.arange(T) * DT
+    kf = kernel_function_device(tgrid, tgrid, KERNEL["type"], KERNEL["param"])
+    ops = Operators(kf["D"][:, :T], None, device=dev)
+    _, X0, hidden = lorenz96_problem(K, T, DT, seed=0, device=dev)        # [K, T] on the device
+    model = OdeModel.lorenz96(K)
+    kw = dict(precondition=not args.no_precondition)
+    if world > 1:
+        from variational_gradient_matching_for_dynamical_systems_b200.distributed import DistributedVGMEngine
+        eng = DistributedVGMEngine(model, ops, None, hidden=hidden, **kw)
+        core = eng.engine
+        eng.set_states_state_major(X0)
+        X0_local = core.X.clone()
+        n_hidden_local = core.plan.n_hidden
+    else:
+        eng = core = VGMEngine(model, ops, None, hidden=hidden, **kw)
+        core.set_states_state_major(X0)
+        X0_local = core.X.clone()
+        n_hidden_local = core.plan.n_hidden
+    del X0
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup0
+    n_hidden_total = len(hidden)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        core.X.copy_(X0_local)
+        return eng.iteration()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.vgm_profile_gemm_enable(1)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    pcg_iters = []
+    e0.record()
+    for _ in range(args.steps):
+        info = step()
+        launches += info["kernel_launches"] + 1
+        pcg_iters.append(info["iterations"])
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    flops, gemm_ms, gemm_n = C.c_double(), C.c_double(), C.c_longlong()
+    lib.vgm_profile_gemm_collect(C.byref(flops), C.byref(gemm_ms), C.byref(gemm_n))
+    lib.vgm_profile_gemm_enable(0)
+    clocks = sampler.stop()
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = n_hidden_total * T * args.steps / (ms * 1e-3)
+    theta = core.get_theta().tolist()
+
+    # ---- end-to-end: host buffers in, host buffers out ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ld = core.ld
+        Xh_in = torch.empty((core.K, ld), dtype=torch.float64, pin_memory=True)
+        Xh_in.copy_(X0_local)
+        Xh_out = torch.empty((core.K, ld), dtype=torch.float64, pin_memory=True)
+        th_h = torch.zeros(max(core.p, 1), dtype=torch.float64, pin_memory=True)
+        h2d = Xh_in.numel() * 8
+        d2h = Xh_out.numel() * 8 + core.p * 8
+
+        def e2e_step():
+            if world > 1:
+                core.X.copy_(Xh_in, non_blocking=True)
+                eng.iteration()
+                Xh_out.copy_(core.X, non_blocking=True)
+                th_h.copy_(core.theta, non_blocking=True)
+                torch.cuda.synchronize()
+            else:
+                core.iteration_host(Xh_in, th_h, Xh_out)
+
+        e2e_step()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax.item())
+        e2e = {"value": n_hidden_total * T * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
+               "api": "vgm_iteration_host (C ABI, pinned host buffers)" if world == 1 else
+                      "DistributedVGMEngine.iteration with pinned host copies per rank"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (FP64 DMMA GEMM) ---------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    fp64_peak = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
+            fp64_peak = json.load(f)["cublas_dgemm_8192_tflops"]
+    except Exception:  # noqa: BLE001
+        fp64_peak = 35.4
+    achieved = flops.value / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value > 0 else None
+    roofline = {"bound": "tensor", "kernel": "vgm::dgemm_nt_kernel (FP64 DMMA)", "achieved": achieved,
+                "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved else None,
+                "traffic": None, "launches": gemm_n.value, "kernel_ms_per_step": gemm_ms.value / args.steps,
+                "share_of_step": gemm_ms.value / ms,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/fp64_peak.json); "
+                               "MEASURED_PEAKS.json has no FP64 entry (hbm_gbs=%s)" % peaks.get("hbm_gbs")}
+    K_h = n_hidden_total
+    F_canon = 2.0 * T * T * K + 2.0 * T * T * K_h + K_h * (T ** 3 / 3.0 + 2.0 * T * T) + 40.0 * T * K
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, total, blas = cpu_port_run(args.cpu_sample_K, T, 1, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "Lorenz96 K=%d (%d hidden), T=%d, 1 iteration of the oracle port (%.1f s)" %
+                         (args.cpu_sample_K, args.cpu_sample_K // 2, T, total), "blas": blas}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Lorenz96 K=%d states (%d hidden, every second state observed+clamped), T=%d; "
+                                   "one step = analytical theta update + full state sweep from the same initial "
+                                   "proxies" % (K, K_h, T),
+                       "kernel": KERNEL, "dt": DT, "solver": "batched PCG (tol 1e-13) as FP64 DMMA GEMMs" +
+                       ("" if not args.no_precondition else ", no preconditioner"),
+                       "parallelism": "state-block x%d" % world,
+                       "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
+                             (n_hidden_local * core.ld * 8 / 1e6)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "pcg_iterations": pcg_iters, "theta": theta, "setup_s": setup_s,
+            "canonical_flops": {"per_step": F_canon, "tflops": F_canon * args.steps / (ms * 1e-3) / 1e12,
+                                "note": "F of SURVEY.md 8(d) (dense Cholesky per state); the executed algorithm is "
+                                        "PCG, see roofline for executed GEMM flops"}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return native_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

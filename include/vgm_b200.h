@@ -88,6 +88,9 @@ typedef struct {
 } vgm_gemm_args;
 int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream);
 int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row of dot_out */
+/* Per-launch CUDA-event timing of the GEMM kernel (used by bench.py for the roofline figure). */
+int vgm_profile_gemm_enable(int on);
+int vgm_profile_gemm_collect(double* flops, double* ms, long long* launches); /* synchronises the device */
 int vgm_transpose(const double* in, int ld_in, double* out, int ld_out, int rows, int cols, vgm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
@@ -192,6 +195,17 @@ int vgm_state_sweep(const vgm_program* prog, const vgm_sweep_plan* plan, const v
                     const vgm_solver_opts* opts, double* X, const double* DX0, const double* theta_star,
                     void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
 
+/* The same sweep in two phases, for callers that must exchange halo rows of X between
+ * dependency levels (multi-GPU state-block partition): prepare once, then call
+ * vgm_state_sweep_level for level = 0 .. n_levels-1 in order.  Before level L > 0 the rows of X
+ * named by plan.live_state for producer level L-1 must hold their updated values (locally
+ * solved, or received from the owning rank).  info accumulates across the calls. */
+int vgm_state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* plan, const vgm_operators* ops,
+                            const double* X, const double* DX0, const double* theta_star, void* ws, size_t ws_bytes,
+                            vgm_sweep_info* info, vgm_stream_t stream);
+int vgm_state_sweep_level(const vgm_sweep_plan* plan, const vgm_operators* ops, const vgm_solver_opts* opts,
+                          double* X, int level, void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
+
 /* One building block of the sweep, exposed for tests: snapshot coefficients
  * Lambda_u = sum_{k!=u} R_uk^2, rhs_u (without the -B_uu^T r_uu term and without live terms),
  * r_uu, R_uu and the R_uk of live pairs (all [n_hidden or n_live_pairs][ld]). */
@@ -221,7 +235,7 @@ int vgm_state_cov(const vgm_program* prog, const vgm_sweep_plan* plan, const vgm
 /* ------------------------------------------------------------------------------------
  * Whole coordinate-ascent iteration with HOST buffers (the end-to-end path):
  *   H2D X -> D.X GEMM -> theta statistics + solve -> state sweep -> D2H X, theta.
- * X_host is [n_states][ld] pinned or pageable host memory, updated in place.
+ * X_host_in / X_host_out are [n_states][ld] pinned or pageable host buffers (may alias).
  */
 typedef struct {
   int n_states, n_odes, n_param;
@@ -237,8 +251,8 @@ int vgm_iteration_device(const vgm_program* prog, const vgm_model_tables* model,
                          double* theta, double* stats, void* ws, size_t ws_bytes, vgm_sweep_info* info,
                          vgm_stream_t stream);
 int vgm_iteration_host(const vgm_program* prog, const vgm_model_tables* model, const vgm_sweep_plan* plan,
-                       const vgm_operators* ops, const vgm_solver_opts* opts, double* X_host, double* theta_host,
-                       double* X_dev, double* DX_dev, double* theta_dev, double* stats_dev,
+                       const vgm_operators* ops, const vgm_solver_opts* opts, const double* X_host_in,
+                       double* X_host_out, double* theta_host, double* X_dev, double* DX_dev, double* theta_dev, double* stats_dev,
                        void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
 
 #ifdef __cplusplus

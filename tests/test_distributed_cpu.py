@@ -1,0 +1,110 @@
+"""Host-side logic of the multi-GPU sharding (no GPU needed): block localisation of the model
+tables / sweep plan, and the halo exchange over a world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from variational_gradient_matching_for_dynamical_systems_b200 import OdeModel, build_host_plan
+from variational_gradient_matching_for_dynamical_systems_b200.distributed import HaloExchange, block_bounds, localize
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_block_bounds_alignment():
+    b = block_bounds(100000, 8, align=2)
+    assert b[0] == 0 and b[-1] == 100000 and all(x % 2 == 0 for x in b)
+    assert max(np.diff(b)) - min(np.diff(b)) <= 2
+    assert block_bounds(10, 3, align=2) == [0, 2, 6, 10]
+
+
+@pytest.mark.parametrize("K,world,allhidden", [(24, 3, False), (20, 2, False), (12, 2, True), (30, 4, False)])
+def test_localize_reproduces_global_structure(K, world, allhidden):
+    model = OdeModel.lorenz96(K)
+    hidden = list(range(K)) if allhidden else list(range(1, K, 2))
+    hp = build_host_plan(model, hidden)
+    bounds = block_bounds(K, world, align=2)
+    rng = np.random.default_rng(0)
+    Xg = rng.standard_normal((K, 7))
+    seen_slots = []
+    pair_slot_g = np.repeat(np.arange(hp.n_hidden), np.diff(hp.pair_ptr))
+    for r in range(world):
+        loc = localize(model, hp, bounds[r], bounds[r + 1])
+        rows = np.concatenate([np.arange(loc.k0, loc.k1), loc.halo_states])
+        Xl = Xg[rows]
+        # theta-side tables: b_k = x_{k+1} x_{k-1} - x_{k-2} x_{k-1} - x_k evaluated through the local gather table
+        s = Xl[loc.ode_idx]                                 # [n_odes, 4, T]
+        b_loc = s[:, 0] * s[:, 2] - s[:, 1] * s[:, 2] - s[:, 3]
+        k = np.arange(loc.k0, loc.k1)
+        b_glob = Xg[(k + 1) % K] * Xg[(k - 1) % K] - Xg[(k - 2) % K] * Xg[(k - 1) % K] - Xg[k]
+        assert np.allclose(b_loc[:loc.n_stats_odes], b_glob)
+        assert np.array_equal(rows[loc.ode_state[:loc.n_stats_odes]], k)
+        # halo width: Lorenz96 reaches 3 states to either side
+        if world > 1:
+            assert len(loc.halo_states) <= 6
+        # sweep plan: same (state, ODE, code, self, live) tuples as the global plan restricted to the block
+        lp = loc.plan
+        g_sel = np.nonzero((hp.slot_state[pair_slot_g] >= loc.k0) & (hp.slot_state[pair_slot_g] < loc.k1))[0]
+        l_slot = np.repeat(np.arange(lp.n_hidden), np.diff(lp.pair_ptr))
+        assert np.array_equal(rows[lp.slot_state[l_slot]], hp.slot_state[pair_slot_g[g_sel]])
+        assert np.array_equal(rows[loc.ode_state[lp.pair_ode]], model.ode_state[hp.pair_ode[g_sel]])
+        assert np.array_equal(lp.pair_code, hp.pair_code[g_sel])
+        assert np.array_equal(lp.pair_self, hp.pair_self[g_sel])
+        assert np.array_equal(lp.pair_live >= 0, hp.pair_live[g_sel] >= 0)
+        # live reads point at the right states and producer levels
+        for e in np.nonzero(lp.pair_live >= 0)[0]:
+            q = lp.pair_live[e]
+            src_state_local = rows[lp.live_state[lp.live_pair_src[q]]]
+            gq = hp.pair_live[g_sel[e]]
+            assert src_state_local == hp.live_state[hp.live_pair_src[gq]]
+            src = lp.live_pair_src[q]
+            lev_src = np.searchsorted(lp.live_level_ptr, src, side="right") - 1
+            lev_cons = lp.level[lp.live_pair_slot[q]]
+            assert lev_src < lev_cons
+        assert lp.n_levels == hp.n_levels and lp.level_ptr[-1] == lp.n_hidden
+        seen_slots += rows[lp.slot_state].tolist()
+    assert sorted(seen_slots) == sorted(hidden)
+
+
+def _halo_worker(rank, world, port, K, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = OdeModel.lorenz96(K)
+        hp = build_host_plan(model, list(range(1, K, 2)))
+        bounds = block_bounds(K, world, align=2)
+        loc = localize(model, hp, bounds[rank], bounds[rank + 1])
+        hx = HaloExchange(loc, bounds)
+        Xg = torch.arange(K * 5, dtype=torch.float64).reshape(K, 5) + 0.25
+        X = torch.zeros((loc.n_rows, 5), dtype=torch.float64)
+        X[:loc.n_owned] = Xg[loc.k0:loc.k1]
+        hx(X)
+        rows = np.concatenate([np.arange(loc.k0, loc.k1), loc.halo_states])
+        ok = bool(torch.equal(X, Xg[torch.as_tensor(rows)]))
+        # the parameter statistics all-reduce: sum of per-rank partial sums == global sum
+        part = X[:loc.n_owned].sum().reshape(1).clone()
+        dist.all_reduce(part)
+        ok = ok and abs(part.item() - Xg.sum().item()) < 1e-9
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_and_allreduce_gloo_world2():
+    world, K = 2, 16
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_halo_worker, args=(world, port, K, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)) and len(ret) == world

@@ -1,0 +1,107 @@
+"""Drop-in for the reference's ``VGM_modules/GP_regression.py`` (same function names,
+positional order, keyword names and defaults), computed on the GPU through libvgm_b200.
+
+* ``kernel_function``            <- GP_regression.py:160-319
+* ``fitting_state_observations`` <- GP_regression.py:33-51
+
+Differences that are deliberate and documented:
+the two ``np.random.multivariate_normal`` draws that only feed a plot (:309-312) and all
+matplotlib side effects are omitted; ``D = dC C^-1`` is obtained from a Cholesky
+factorisation on the device instead of LAPACK ``gesv`` (agreement ~ cond(C) * eps).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_KTYPES = {"rbf": _lib.KERNEL_RBF, "RQ": _lib.KERNEL_RQ}
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def kernel_function_device(time_points, time_points2, kernel_type="RQ", kernel_param=[0.1, 2, 5], batch_params=None,
+                           want_inverse=False):
+    """Device-resident version: returns a dict of padded CUDA tensors
+    ``D, A, C, dC, ddC, Cobs, Cso`` (+ ``Cinv``), each ``[rows, ld]`` with ``ld`` = columns
+    rounded up to 8, plus ``T``/``T2``."""
+    if kernel_type not in _KTYPES:
+        raise NotImplementedError(
+            "kernel_type %r: the B200 path implements the closed-form 'rbf' and 'RQ' kernels "
+            "(GP_regression.py:176-179,205-209)" % (kernel_type,))
+    lib = _lib.load()
+    dev = _lib.require_cuda()
+    t = torch.as_tensor(np.asarray(time_points, dtype=np.float64), device=dev)
+    t2 = torch.as_tensor(np.asarray(time_points2, dtype=np.float64), device=dev)
+    T, T2 = t.numel(), t2.numel()
+    ld, ld2 = _round_up(max(T, 1), 8), _round_up(max(T2, 1), 8)
+    z = lambda r, l: torch.zeros((max(r, 1), l), dtype=torch.float64, device=dev)
+    out = dict(T=T, T2=T2, ld=ld, ld2=ld2, C=z(T, ld), dC=z(T, ld), ddC=z(T, ld), Cobs=z(T2, ld2), Cso=z(T, ld2),
+               D=z(T, ld), A=z(T, ld))
+    par = (C.c_double * len(kernel_param))(*[float(v) for v in kernel_param])
+    s = _lib.stream_ptr()
+    _lib.check(lib.vgm_kernel_build(_KTYPES[kernel_type], par, len(kernel_param), t.data_ptr(), T, t2.data_ptr(), T2,
+                                    ld, ld2, out["C"].data_ptr(), out["dC"].data_ptr(), out["ddC"].data_ptr(),
+                                    out["Cobs"].data_ptr(), out["Cso"].data_ptr(), s))
+    n = lib.vgm_gm_operators_ws_bytes(T, ld)
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    cinv = z(T, ld) if want_inverse else None
+    _lib.check(lib.vgm_gm_operators(out["C"].data_ptr(), out["dC"].data_ptr(), out["ddC"].data_ptr(), T, ld, 1,
+                                    out["D"].data_ptr(), out["A"].data_ptr(), _lib.ptr(cinv), ws.data_ptr(), n, s))
+    if want_inverse:
+        out["Cinv"] = cinv
+    return out
+
+
+def kernel_function(time_points, time_points2, kernel_type='RQ', kernel_param=[0.1, 2, 5]):
+    '''Populates the GP covariance matrix and it's derivatives (GP_regression.py:160).
+    Returns ``cov_diff_times_inv_cov, eps_cov, cov, cov_obs, cov_state_obs`` as numpy arrays.'''
+    # error handling, verbatim behaviour of GP_regression.py:168-171
+    if type(time_points) is not np.ndarray:
+        raise ValueError('time points is not a numpy array')
+    elif len(time_points.shape) > 1:
+        raise ValueError('time points must be a one dimensional numpy array')
+    o = kernel_function_device(time_points, np.asarray(time_points2, dtype=float), kernel_type, kernel_param)
+    T, T2 = o["T"], o["T2"]
+    c = lambda m, r, n: m[:r, :n].cpu().numpy()
+    return c(o["D"], T, T), c(o["A"], T, T), c(o["C"], T, T), c(o["Cobs"], T2, T2), c(o["Cso"], T, T2)
+
+
+def fitting_state_observations(observations, hidden_states, SNR, time_points, cov, cov_obs, cov_func_obs,
+                               fig_shape=(10, 8)):
+    """GP fit of the observed states = initial state proxy (GP_regression.py:33-51).
+
+    Reproduces the reference's accumulating-noise behaviour (``cov_obs`` is reassigned inside
+    the loop at :42, so observed state i sees sum_{j<=i} sigma_j^2), leaves unobserved states
+    at zero (:38) and returns ``(state_pred_mean DataFrame T x K, state_pred_inv_cov)``.
+    The solves run on the device: SPD inverse by Cholesky (vgm_spd_inverse) + DMMA GEMMs."""
+    import pandas as pd
+    lib = _lib.load()
+    dev = _lib.require_cuda()
+    Y = np.asarray(observations.values, dtype=np.float64)
+    obs_variance = (np.mean(Y, axis=0) / SNR) ** 2
+    T, T2 = len(time_points), Y.shape[0]
+    names = list(map(str, hidden_states))
+    mean = np.zeros((T, len(names)))
+    ld2 = _round_up(T2, 8)
+    Co = torch.zeros((T2, ld2), dtype=torch.float64, device=dev)
+    Co[:, :T2] = torch.as_tensor(np.asarray(cov_obs, dtype=np.float64), device=dev)
+    Cso = torch.as_tensor(np.asarray(cov_func_obs, dtype=np.float64), device=dev)
+    n = lib.vgm_gm_operators_ws_bytes(T2, ld2)
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    inv = torch.zeros_like(Co)
+    eye = torch.eye(T2, dtype=torch.float64, device=dev)
+    for i, state in enumerate(list(observations.columns)):
+        Co[:, :T2] += obs_variance[i] * eye
+        _lib.check(lib.vgm_spd_inverse(Co.data_ptr(), T2, ld2, inv.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr()))
+        y = torch.as_tensor(Y[:, i], device=dev)
+        mean[:, names.index(str(state))] = (Cso @ (inv[:, :T2] @ y)).cpu().numpy()
+    pred_cov = np.asarray(cov, dtype=np.float64) - (Cso @ (inv[:, :T2] @ Cso.t())).cpu().numpy()
+    state_pred_inv_cov = np.linalg.pinv(pred_cov)      # unused by the analytical path (:46)
+    state_pred_mean = pd.DataFrame(mean, columns=names, index=time_points).rename_axis('time')
+    return state_pred_mean, state_pred_inv_cov

@@ -82,6 +82,8 @@ SIGNATURES = {
                                    c_dp, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "vgm_dgemm_nt": (C.c_int, [_P(GemmArgs), C.c_void_p]),
     "vgm_dgemm_dot_tiles": (C.c_int, [C.c_int, C.c_int]),
+    "vgm_profile_gemm_enable": (C.c_int, [C.c_int]),
+    "vgm_profile_gemm_collect": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
     "vgm_transpose": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vgm_gm_operators_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vgm_gm_operators": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_size_t,
@@ -98,6 +100,10 @@ SIGNATURES = {
     "vgm_state_sweep_ws_bytes": (C.c_size_t, [_P(SweepPlan)]),
     "vgm_state_sweep": (C.c_int, [C.c_void_p, _P(SweepPlan), _P(Operators), _P(SolverOpts), c_dp, c_dp, c_dp, c_dp,
                                   C.c_size_t, _P(SweepInfo), C.c_void_p]),
+    "vgm_state_sweep_prepare": (C.c_int, [C.c_void_p, _P(SweepPlan), _P(Operators), c_dp, c_dp, c_dp, c_dp, C.c_size_t,
+                                          _P(SweepInfo), C.c_void_p]),
+    "vgm_state_sweep_level": (C.c_int, [_P(SweepPlan), _P(Operators), _P(SolverOpts), c_dp, C.c_int, c_dp, C.c_size_t,
+                                        _P(SweepInfo), C.c_void_p]),
     "vgm_state_assemble": (C.c_int, [C.c_void_p, _P(SweepPlan), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                      C.c_void_p]),
     "vgm_pcg_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -110,7 +116,7 @@ SIGNATURES = {
     "vgm_iteration_device": (C.c_int, [C.c_void_p, _P(ModelTables), _P(SweepPlan), _P(Operators), _P(SolverOpts),
                                        c_dp, c_dp, c_dp, c_dp, c_dp, C.c_size_t, _P(SweepInfo), C.c_void_p]),
     "vgm_iteration_host": (C.c_int, [C.c_void_p, _P(ModelTables), _P(SweepPlan), _P(Operators), _P(SolverOpts),
-                                     c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_size_t, _P(SweepInfo),
+                                     c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_size_t, _P(SweepInfo),
                                      C.c_void_p]),
 }
 

@@ -75,18 +75,18 @@ extern "C" int vgm_iteration_device(const vgm_program* prog, const vgm_model_tab
 }
 
 extern "C" int vgm_iteration_host(const vgm_program* prog, const vgm_model_tables* model, const vgm_sweep_plan* plan,
-                                  const vgm_operators* ops, const vgm_solver_opts* opts, double* X_host,
-                                  double* theta_host, double* X_dev, double* DX_dev, double* theta_dev,
+                                  const vgm_operators* ops, const vgm_solver_opts* opts, const double* X_host_in,
+                                  double* X_host_out, double* theta_host, double* X_dev, double* DX_dev, double* theta_dev,
                                   double* stats_dev, void* ws, size_t ws_bytes, vgm_sweep_info* info,
                                   vgm_stream_t stream) {
-  VGM_REQUIRE(model && plan && X_host && theta_host && X_dev, "null argument");
+  VGM_REQUIRE(model && plan && X_host_in && X_host_out && theta_host && X_dev, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = (size_t)model->n_states * plan->ld * sizeof(double);
-  VGM_CUDA_OK(cudaMemcpyAsync(X_dev, X_host, bytes, cudaMemcpyHostToDevice, s));
+  VGM_CUDA_OK(cudaMemcpyAsync(X_dev, X_host_in, bytes, cudaMemcpyHostToDevice, s));
   int rc = vgm_iteration_device(prog, model, plan, ops, opts, X_dev, DX_dev, theta_dev, stats_dev, ws, ws_bytes, info,
                                 stream);
   if (rc != VGM_OK && rc != VGM_ENOTCONV) return rc;
-  VGM_CUDA_OK(cudaMemcpyAsync(X_host, X_dev, bytes, cudaMemcpyDeviceToHost, s));
+  VGM_CUDA_OK(cudaMemcpyAsync(X_host_out, X_dev, bytes, cudaMemcpyDeviceToHost, s));
   VGM_CUDA_OK(cudaMemcpyAsync(theta_host, theta_dev, model->n_param * sizeof(double), cudaMemcpyDeviceToHost, s));
   VGM_CUDA_OK(cudaStreamSynchronize(s));
   return rc;

@@ -13,6 +13,8 @@
 // (a T x T operator, 8 MB at T=1000) stays L2 resident; the A operand streams from HBM once
 // per column-tile sweep.  Operands are staged through a 4-deep cp.async ring in shared
 // memory with a +4 double row pad (conflict-free 64-bit fragment loads).
+#include <vector>
+
 #include "vgm_common.cuh"
 
 namespace vgm {
@@ -224,7 +226,38 @@ int gemm_dot_tiles(int M, int N) {
   return ceil_div(M, CfgBig::BN);
 }
 
+// ---- optional per-launch CUDA-event profile of the GEMM (bench.py roofline) ----------------
+struct GemmProfile {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop), reused across collections
+  size_t used = 0;
+  double flops = 0.0;
+  long long launches = 0;
+};
+static GemmProfile g_prof;
+
+static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s);
+
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s) {
+  if (!g_prof.enabled || a.N == 0) return dgemm_dispatch(a, s);
+  if (g_prof.used + 2 > g_prof.ev.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      VGM_CUDA_OK(cudaEventCreate(&e));
+      g_prof.ev.push_back(e);
+    }
+  }
+  cudaEvent_t e0 = g_prof.ev[g_prof.used], e1 = g_prof.ev[g_prof.used + 1];
+  VGM_CUDA_OK(cudaEventRecord(e0, s));
+  int rc = dgemm_dispatch(a, s);
+  VGM_CUDA_OK(cudaEventRecord(e1, s));
+  g_prof.used += 2;
+  g_prof.flops += 2.0 * a.N * a.M * a.K;
+  g_prof.launches += 1;
+  return rc;
+}
+
+static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s) {
   VGM_REQUIRE(a.A && a.B && a.C, "null operand");
   VGM_REQUIRE(a.N >= 0 && a.M > 0 && a.K > 0, "bad shape");
   VGM_REQUIRE((a.lda % 2) == 0 && (a.ldb % 2) == 0 && (a.ldc % 2) == 0, "leading dimensions must be even (16-byte rows)");
@@ -243,6 +276,33 @@ extern "C" int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream) {
     return VGM_EINVAL;
   }
   return vgm::dgemm_nt(*args, (cudaStream_t)stream);
+}
+
+extern "C" int vgm_profile_gemm_enable(int on) {
+  vgm::g_prof.enabled = (on != 0);
+  vgm::g_prof.used = 0;
+  vgm::g_prof.flops = 0.0;
+  vgm::g_prof.launches = 0;
+  return VGM_OK;
+}
+
+// Sum of the CUDA-event durations of every DGEMM launched since the last enable/collect
+// (synchronises the device), the algorithmic flops 2*N*M*K of those launches and their count.
+extern "C" int vgm_profile_gemm_collect(double* flops, double* ms, long long* launches) {
+  VGM_CUDA_OK(cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < vgm::g_prof.used; i += 2) {
+    float t = 0.f;
+    VGM_CUDA_OK(cudaEventElapsedTime(&t, vgm::g_prof.ev[i], vgm::g_prof.ev[i + 1]));
+    total += t;
+  }
+  if (flops) *flops = vgm::g_prof.flops;
+  if (ms) *ms = total;
+  if (launches) *launches = vgm::g_prof.launches;
+  vgm::g_prof.used = 0;
+  vgm::g_prof.flops = 0.0;
+  vgm::g_prof.launches = 0;
+  return VGM_OK;
 }
 
 extern "C" int vgm_dgemm_dot_tiles(int M, int N) { return vgm::gemm_dot_tiles(M, N); }

@@ -441,72 +441,85 @@ static int sweep_carve(void* ws, size_t ws_bytes, const vgm_sweep_plan* pl, Swee
   return pcg_carve(p, ws_bytes - used, pl->n_hidden, pl->T, pl->ld, w.pcg);
 }
 
-static int state_sweep(const vgm_program* prog, const vgm_sweep_plan* pl, const vgm_operators* ops,
-                       const vgm_solver_opts* opts, double* X, const double* DX0, const double* theta_star, void* ws,
-                       size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+// Phase 1 of a sweep: snapshot coefficients + the -B_uu^T r_uu term of every hidden state.
+static int state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* pl, const vgm_operators* ops,
+                               const double* X, const double* DX0, const double* theta_star, void* ws,
+                               size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
   VGM_REQUIRE(prog && pl && ops && X && DX0 && theta_star, "null argument");
   VGM_REQUIRE(pl->T > 0 && pl->ld >= pl->T && (pl->ld % 2) == 0, "plan shape");
   if (info) memset(info, 0, sizeof(*info));
   if (pl->n_hidden == 0) return VGM_OK;
   SweepWs w;
   VGM_TRY(sweep_carve(ws, ws_bytes, pl, w));
+  const int T = pl->T, ld = pl->ld;
+  // snapshot coefficients for every hidden state (R, r evaluated on the sweep-start X, :191)
+  VGM_TRY(program_state_assemble(prog, pl, X, DX0, theta_star, w.Lambda, w.rhs, w.ruu, w.Ruu, w.Rlive, s));
+  // rhs += -B_uu^T r_uu = D^T r_uu - R_uu o r_uu                                    (:231)
+  vgm_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = w.ruu; g.B = ops->DT; g.C = w.rhs; g.C0 = w.rhs;
+  g.lda = g.ldb = g.ldc = ld;
+  g.N = pl->n_hidden; g.M = T; g.K = T;
+  g.alpha = 1.0; g.beta = 1.0;
+  g.U1 = pl->ruu_const ? nullptr : w.Ruu;
+  g.V1 = w.ruu;
+  g.g1 = pl->ruu_const ? -pl->ruu_value : -1.0;
+  VGM_TRY(dgemm_nt(g, s));
+  if (info) { info->gemm_calls += 1; info->kernel_launches += 2; }
+  return VGM_OK;
+}
+
+// Phase 2, once per dependency level (in order): refresh D x_k of the states updated in the
+// previous level that this level reads live (:225), patch rhs, solve the level's systems.
+static int state_sweep_level(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts,
+                             double* X, int lev, void* ws, size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+  VGM_REQUIRE(pl && ops && X && lev >= 0 && lev < pl->n_levels, "level out of range");
+  if (pl->n_hidden == 0) return VGM_OK;
+  SweepWs w;
+  VGM_TRY(sweep_carve(ws, ws_bytes, pl, w));
   Counters cnt;
   const int T = pl->T, ld = pl->ld;
-
-  // 1. snapshot coefficients for every hidden state (R, r evaluated on the sweep-start X, :191)
-  VGM_TRY(program_state_assemble(prog, pl, X, DX0, theta_star, w.Lambda, w.rhs, w.ruu, w.Ruu, w.Rlive, s));
-  cnt.launches += 1;
-
-  // 2. rhs += -B_uu^T r_uu = D^T r_uu - R_uu o r_uu                                 (:231)
-  {
-    vgm_gemm_args g;
-    memset(&g, 0, sizeof(g));
-    g.A = w.ruu; g.B = ops->DT; g.C = w.rhs; g.C0 = w.rhs;
-    g.lda = g.ldb = g.ldc = ld;
-    g.N = pl->n_hidden; g.M = T; g.K = T;
-    g.alpha = 1.0; g.beta = 1.0;
-    g.U1 = pl->ruu_const ? nullptr : w.Ruu;
-    g.V1 = w.ruu;
-    g.g1 = pl->ruu_const ? -pl->ruu_value : -1.0;
-    VGM_TRY(dgemm_nt(g, s));
-    cnt.gemm += 1; cnt.launches += 1;
+  if (lev > 0 && pl->n_live > 0) {
+    const int l0 = pl->live_level_ptr_host[lev - 1], l1 = pl->live_level_ptr_host[lev];
+    if (l1 > l0) {
+      vgm_gemm_args g;
+      memset(&g, 0, sizeof(g));
+      g.A = X; g.B = ops->D; g.C = w.DXlive + (size_t)l0 * ld;
+      g.lda = g.ldb = g.ldc = ld;
+      g.N = l1 - l0; g.M = T; g.K = T;
+      g.rowsA = pl->live_state + l0;
+      g.alpha = 1.0;
+      VGM_TRY(dgemm_nt(g, s));
+      cnt.gemm += 1; cnt.launches += 1;
+    }
   }
+  if (lev > 0 && pl->n_live_pairs > 0) {
+    const int q0 = pl->live_pair_level_ptr_host[lev], q1 = pl->live_pair_level_ptr_host[lev + 1];
+    if (q1 > q0) {
+      add_live_terms_kernel<<<q1 - q0, row_threads(T), 0, s>>>(pl->live_pair_slot, pl->live_pair_src, q0, w.Rlive,
+                                                               w.DXlive, T, ld, w.rhs);
+      VGM_LAUNCH_OK();
+      cnt.launches += 1;
+    }
+  }
+  const int r0 = pl->level_ptr_host[lev], r1 = pl->level_ptr_host[lev + 1];
+  int rc = pcg_solve(ops, pl->ruu_const, w.Ruu, w.Lambda, w.rhs, X, pl->slot_state, pl->slot_has_self,
+                     pl->level_slots + r0, r1 - r0, T, ld, opts, w.pcg, info, cnt, s);
+  if (info) {
+    info->gemm_calls += cnt.gemm;
+    info->kernel_launches += cnt.launches;
+  }
+  return rc;
+}
 
-  // 3. dependency levels in the reference's update order
+static int state_sweep(const vgm_program* prog, const vgm_sweep_plan* pl, const vgm_operators* ops,
+                       const vgm_solver_opts* opts, double* X, const double* DX0, const double* theta_star, void* ws,
+                       size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+  VGM_TRY(state_sweep_prepare(prog, pl, ops, X, DX0, theta_star, ws, ws_bytes, info, s));
   int rc = VGM_OK;
   for (int lev = 0; lev < pl->n_levels; ++lev) {
-    const int r0 = pl->level_ptr_host[lev], r1 = pl->level_ptr_host[lev + 1];
-    if (lev > 0 && pl->n_live_pairs > 0) {
-      const int q0 = pl->live_pair_level_ptr_host[lev], q1 = pl->live_pair_level_ptr_host[lev + 1];
-      if (q1 > q0) {
-        add_live_terms_kernel<<<q1 - q0, row_threads(T), 0, s>>>(pl->live_pair_slot, pl->live_pair_src, q0, w.Rlive,
-                                                                 w.DXlive, T, ld, w.rhs);
-        VGM_LAUNCH_OK();
-        cnt.launches += 1;
-      }
-    }
-    int r = pcg_solve(ops, pl->ruu_const, w.Ruu, w.Lambda, w.rhs, X, pl->slot_state, pl->slot_has_self,
-                      pl->level_slots + r0, r1 - r0, T, ld, opts, w.pcg, info, cnt, s);
+    int r = state_sweep_level(pl, ops, opts, X, lev, ws, ws_bytes, info, s);
     if (r == VGM_ENOTCONV) rc = r; else if (r != VGM_OK) return r;
-    if (pl->n_live > 0) {
-      const int l0 = pl->live_level_ptr_host[lev], l1 = pl->live_level_ptr_host[lev + 1];
-      if (l1 > l0) {
-        // D x_k of the states just updated that later states read live (:225)
-        vgm_gemm_args g;
-        memset(&g, 0, sizeof(g));
-        g.A = X; g.B = ops->D; g.C = w.DXlive + (size_t)l0 * ld;
-        g.lda = g.ldb = g.ldc = ld;
-        g.N = l1 - l0; g.M = T; g.K = T;
-        g.rowsA = pl->live_state + l0;
-        g.alpha = 1.0;
-        VGM_TRY(dgemm_nt(g, s));
-        cnt.gemm += 1; cnt.launches += 1;
-      }
-    }
-  }
-  if (info) {
-    info->gemm_calls = cnt.gemm;
-    info->kernel_launches = cnt.launches;
   }
   return rc;
 }
@@ -609,6 +622,18 @@ extern "C" int vgm_pcg_solve(const vgm_operators* ops, int ruu_const, const doub
                     (cudaStream_t)stream);
   if (info) { info->gemm_calls = cnt.gemm; info->kernel_launches = cnt.launches; }
   return r;
+}
+
+extern "C" int vgm_state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* plan, const vgm_operators* ops,
+                                       const double* X, const double* DX0, const double* theta_star, void* ws,
+                                       size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream) {
+  return state_sweep_prepare(prog, plan, ops, X, DX0, theta_star, ws, ws_bytes, info, (cudaStream_t)stream);
+}
+
+extern "C" int vgm_state_sweep_level(const vgm_sweep_plan* plan, const vgm_operators* ops, const vgm_solver_opts* opts,
+                                     double* X, int level, void* ws, size_t ws_bytes, vgm_sweep_info* info,
+                                     vgm_stream_t stream) {
+  return state_sweep_level(plan, ops, opts, X, level, ws, ws_bytes, info, (cudaStream_t)stream);
 }
 
 extern "C" size_t vgm_state_sweep_ws_bytes(const vgm_sweep_plan* plan) { return plan ? sweep_ws_bytes(plan) : 0; }

@@ -1,0 +1,243 @@
+"""Multi-GPU sharding of the VGM loop: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink on the B200 box, gloo in CPU tests) for the two exchanges the path really has
+(the reference itself is single-process):
+
+* **state blocks** (Lorenz96 K=100k): rank g owns a contiguous block of states; before a sweep
+  and between dependency levels the few boundary rows of X that neighbours read (3 on each
+  side for Lorenz96) are refreshed with one small all-gather;
+* **trajectory batches**: trajectories are split across ranks, no halo at all;
+
+and, in both cases, one all-reduce (sum) of the ODE-parameter sufficient statistics
+``[m | S]`` (p + p^2 doubles) per iteration, after which every rank solves the p x p system
+redundantly.  Every rank executes the *global* dependency levels in the reference's order, so
+the result is the single-GPU result (up to the summation order of the all-reduce).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .codegen import HostPlan, OdeModel, build_host_plan
+
+
+def block_bounds(n_items, world, align=1):
+    """Contiguous, nearly equal blocks [b[g], b[g+1]) with boundaries on multiples of ``align``."""
+    units = n_items // align
+    b = [(units * g // world) * align for g in range(world)] + [n_items]
+    return b
+
+
+class Localized:
+    """Result of :func:`localize` (everything a rank needs, all host-side NumPy)."""
+
+
+def localize(model: OdeModel, hp: HostPlan, k0: int, k1: int) -> Localized:
+    """Restrict a global model + sweep plan to the states [k0, k1) owned by one rank.
+
+    Local X rows: owned states first (local row = k - k0), then the halo states (ascending
+    global index) that owned ODE rows / owned hidden states read.  Local ODE rows: owned ODEs
+    first (they alone enter the theta statistics), then the neighbours' ODEs that couple to an
+    owned hidden state (needed for R_uk, r_uk and D x_k of those pairs)."""
+    K = model.K
+    arity_of = np.array([c.arity for c in model.classes], dtype=np.int64)
+    slot_state = np.asarray(hp.slot_state, dtype=np.int64)
+    loc_slots = np.nonzero((slot_state >= k0) & (slot_state < k1))[0]
+    slot_map = np.full(hp.n_hidden, -1, dtype=np.int64)
+    slot_map[loc_slots] = np.arange(len(loc_slots))
+    pair_slot = np.repeat(np.arange(hp.n_hidden), np.diff(hp.pair_ptr))
+    pair_sel = np.nonzero(slot_map[pair_slot] >= 0)[0]
+    owned_odes = np.arange(k0, k1, dtype=np.int64)
+    extra_odes = np.setdiff1d(np.unique(hp.pair_ode[pair_sel]).astype(np.int64), owned_odes)
+    odes = np.concatenate([owned_odes, extra_odes])
+    ode_map = np.full(K, -1, dtype=np.int64)
+    ode_map[odes] = np.arange(len(odes))
+    # states referenced by those ODE rows
+    idx = model.ode_idx[odes].astype(np.int64)
+    valid = np.arange(model.arity)[None, :] < arity_of[model.ode_class[odes]][:, None]
+    # live sources read by local consumers
+    live_e = pair_sel[hp.pair_live[pair_sel] >= 0]
+    src_global_state = np.asarray(hp.live_state, dtype=np.int64)[hp.live_pair_src[hp.pair_live[live_e]]] \
+        if len(live_e) else np.zeros(0, dtype=np.int64)
+    needed = np.unique(np.concatenate([idx[valid], model.ode_state[odes].astype(np.int64), src_global_state]))
+    halo = needed[(needed < k0) | (needed >= k1)]
+    row_map = np.full(K, -1, dtype=np.int64)
+    row_map[k0:k1] = np.arange(k1 - k0)
+    row_map[halo] = (k1 - k0) + np.arange(len(halo))
+    out = Localized()
+    out.k0, out.k1 = k0, k1
+    out.n_owned = k1 - k0
+    out.halo_states = halo
+    out.n_rows = (k1 - k0) + len(halo)
+    out.ode_class = model.ode_class[odes].astype(np.int32)
+    li = np.where(valid, row_map[idx], 0)
+    assert (li >= 0).all()
+    out.ode_idx = li.astype(np.int32)
+    out.ode_state = row_map[model.ode_state[odes]].astype(np.int32)
+    out.n_stats_odes = len(owned_odes)
+    # ---- local sweep plan (global levels are kept so that all ranks step through them together)
+    lp = HostPlan()
+    nh = len(loc_slots)
+    lp.n_hidden = nh
+    lp.slot_state = row_map[slot_state[loc_slots]].astype(np.int32)
+    counts = np.diff(hp.pair_ptr)[loc_slots]
+    lp.pair_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    lp.n_pairs = len(pair_sel)
+    lp.pair_ode = ode_map[hp.pair_ode[pair_sel]].astype(np.int32)
+    lp.pair_code = hp.pair_code[pair_sel].astype(np.int32)
+    lp.pair_self = hp.pair_self[pair_sel].astype(np.int32)
+    lp.slot_has_self = hp.slot_has_self[loc_slots].astype(np.int32)
+    lp.n_levels = hp.n_levels
+    lp.level = hp.level[loc_slots]
+    order = np.lexsort((np.arange(nh), lp.level))
+    lp.level_slots = order.astype(np.int32)
+    lptr = np.zeros(hp.n_levels + 1, dtype=np.int64)
+    np.add.at(lptr, lp.level + 1, 1)
+    lp.level_ptr = np.cumsum(lptr).astype(np.int32)
+    # live pairs: keep the global ordering (by consumer level, slot, k)
+    g_live_ord = hp.pair_live[pair_sel]                       # -1 or global live-pair ordinal
+    is_live = g_live_ord >= 0
+    live_local_idx = np.nonzero(is_live)[0]
+    o = np.argsort(g_live_ord[live_local_idx], kind="stable")
+    live_local_idx = live_local_idx[o]
+    lp.pair_live = np.full(len(pair_sel), -1, dtype=np.int32)
+    lp.pair_live[live_local_idx] = np.arange(len(live_local_idx), dtype=np.int32)
+    lp.n_live_pairs = len(live_local_idx)
+    g_ord = g_live_ord[live_local_idx]
+    consumer_slot_local = slot_map[pair_slot[pair_sel[live_local_idx]]]
+    lp.live_pair_slot = consumer_slot_local.astype(np.int32)
+    g_src = hp.live_pair_src[g_ord] if len(g_ord) else np.zeros(0, dtype=np.int64)   # global live-buffer slot
+    # producer level of every global live source
+    g_src_level = np.zeros(hp.n_live, dtype=np.int64)
+    for lev in range(hp.n_levels):
+        g_src_level[hp.live_level_ptr[lev]:hp.live_level_ptr[lev + 1]] = lev
+    used_src = np.unique(g_src)                               # ascending = grouped by producer level
+    src_map = {int(s): i for i, s in enumerate(used_src.tolist())}
+    lp.n_live = len(used_src)
+    lp.live_state = row_map[np.asarray(hp.live_state, dtype=np.int64)[used_src]].astype(np.int32) \
+        if len(used_src) else np.zeros(0, dtype=np.int32)
+    llp = np.zeros(hp.n_levels + 1, dtype=np.int64)
+    if len(used_src):
+        np.add.at(llp, g_src_level[used_src] + 1, 1)
+    lp.live_level_ptr = np.cumsum(llp).astype(np.int32)
+    lp.live_pair_src = np.array([src_map[int(s)] for s in g_src.tolist()], dtype=np.int32)
+    lpl = np.zeros(hp.n_levels + 1, dtype=np.int64)
+    if lp.n_live_pairs:
+        np.add.at(lpl, lp.level[consumer_slot_local] + 1, 1)
+    lp.live_pair_level_ptr = np.cumsum(lpl).astype(np.int32)
+    lp.ruu_const, lp.ruu_value = hp.ruu_const, hp.ruu_value
+    out.plan = lp
+    out.hidden_global = slot_state[loc_slots]
+    return out
+
+
+class HaloExchange:
+    """Refresh of the halo rows of X: every rank contributes the owned rows that any other
+    rank reads (padded to a common count) to one all-gather and then picks its halo rows."""
+
+    def __init__(self, loc: Localized, bounds, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        halos = [None] * self.world
+        dist.all_gather_object(halos, loc.halo_states.tolist(), group=group)
+        bounds = np.asarray(bounds)
+        send = [[] for _ in range(self.world)]          # owned states each rank must publish
+        for r, hs in enumerate(halos):
+            for s in hs:
+                owner = int(np.searchsorted(bounds, s, side="right") - 1)
+                send[owner].append(int(s))
+        send = [sorted(set(v)) for v in send]
+        self.n_pub = max(1, max(len(v) for v in send))
+        self.pub_rows_local = np.array([s - loc.k0 for s in send[self.rank]], dtype=np.int64)
+        pos = [{s: i for i, s in enumerate(v)} for v in send]
+        owners = [int(np.searchsorted(bounds, s, side="right") - 1) for s in loc.halo_states.tolist()]
+        self.src_flat = np.array([o * self.n_pub + pos[o][int(s)] for o, s in zip(owners, loc.halo_states.tolist())],
+                                 dtype=np.int64)
+        self.halo_rows_local = loc.n_owned + np.arange(len(loc.halo_states), dtype=np.int64)
+        self._buf = None
+
+    def __call__(self, X):
+        """X: [n_rows, ld] tensor of this rank (owned rows first); halo rows are overwritten."""
+        if self.world == 1 and len(self.src_flat) == 0:
+            return
+        ld = X.shape[1]
+        if self._buf is None or self._buf[0].shape[1] != ld or self._buf[0].device != X.device:
+            self._buf = (torch.zeros((self.n_pub, ld), dtype=X.dtype, device=X.device),
+                         torch.zeros((self.world * self.n_pub, ld), dtype=X.dtype, device=X.device),
+                         torch.as_tensor(self.pub_rows_local, device=X.device),
+                         torch.as_tensor(self.src_flat, device=X.device),
+                         torch.as_tensor(self.halo_rows_local, device=X.device))
+        pub, gathered, pub_idx, src_idx, halo_idx = self._buf
+        if len(self.pub_rows_local):
+            pub[:len(self.pub_rows_local)] = X.index_select(0, pub_idx)
+        dist.all_gather_into_tensor(gathered, pub, group=self.group)
+        if len(self.src_flat):
+            X.index_copy_(0, halo_idx, gathered.index_select(0, src_idx))
+
+
+class DistributedVGMEngine:
+    """State-block (or trajectory-batch) sharded VGM engine; same iteration as ``VGMEngine``."""
+
+    def __init__(self, model: OdeModel, D, A=None, hidden=None, schedule="reference", align=2, group=None, **kw):
+        from .engine import LocalProblem, VGMEngine
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.model = model
+        if hidden is None:
+            hidden = np.arange(model.K)
+        hp = build_host_plan(model, hidden, schedule=schedule)
+        self.global_plan = hp
+        self.bounds = block_bounds(model.K, self.world, align=align)
+        k0, k1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.loc = localize(model, hp, k0, k1)
+        prob = LocalProblem(self.loc.n_rows, self.loc.n_stats_odes, self.loc.ode_class, self.loc.ode_idx,
+                            self.loc.ode_state, self.loc.plan, model.p)
+        self.engine = VGMEngine(model, D, A, problem=prob, **kw)
+        self.halo = HaloExchange(self.loc, self.bounds, group=group)
+        self.n_hidden_global = hp.n_hidden
+        self.n_levels = hp.n_levels
+
+    # ---- data ------------------------------------------------------------------------------------
+    def set_states_state_major(self, X_global_KT):
+        """Every rank passes the same global [K, T] array (or at least its own block + halo)."""
+        e, loc = self.engine, self.loc
+        rows = np.concatenate([np.arange(loc.k0, loc.k1), loc.halo_states]).astype(np.int64)
+        Xg = torch.as_tensor(X_global_KT)
+        idx = torch.as_tensor(rows, device=Xg.device)
+        e.X.zero_()
+        e.X[:, :e.T] = Xg.index_select(0, idx)[:, :e.T].to(e.dev, dtype=torch.float64)
+
+    def owned_states(self):
+        """[n_owned, T] tensor of this rank's block."""
+        return self.engine.X[:self.loc.n_owned, :self.engine.T]
+
+    def gather_states(self):
+        """Global [K, T] tensor on every rank (for tests/reporting)."""
+        e = self.engine
+        sizes = [self.bounds[g + 1] - self.bounds[g] for g in range(self.world)]
+        mx = max(sizes)
+        mine = torch.zeros((mx, e.T), dtype=torch.float64, device=e.dev)
+        mine[:self.loc.n_owned] = self.owned_states()
+        allb = torch.zeros((self.world * mx, e.T), dtype=torch.float64, device=e.dev)
+        dist.all_gather_into_tensor(allb, mine, group=self.group)
+        return torch.cat([allb[g * mx:g * mx + sizes[g]] for g in range(self.world)], 0)
+
+    # ---- one coordinate-ascent iteration ---------------------------------------------------------------
+    def iteration(self, allow_unconverged=False):
+        e = self.engine
+        self.halo(e.X)                                   # neighbours' boundary rows (snapshot)
+        e.compute_DX()
+        e.param_stats()
+        dist.all_reduce(e.stats, op=dist.ReduceOp.SUM, group=self.group)
+        e.param_solve()
+        e.sweep_prepare()
+        for lev in range(self.n_levels):
+            if lev > 0:
+                self.halo(e.X)                           # rows updated by their owners in level lev-1
+            e.sweep_level(lev, allow_unconverged=allow_unconverged)
+        return e.last_info
+
+    def get_theta(self):
+        return self.engine.get_theta()

@@ -94,9 +94,8 @@ class Operators:
 class DevicePlan:
     """``vgm_sweep_plan`` with its device/host arrays kept alive."""
 
-    def __init__(self, model: OdeModel, hidden, T, ld, tables, couplings=None, schedule="reference", device=None):
+    def __init__(self, hp, T, ld, tables, device=None):
         dev = device or _lib.require_cuda()
-        hp = build_host_plan(model, hidden, couplings=couplings, schedule=schedule)
         self.host = hp
         keep = self._keep = {}
         for name in ("slot_state", "pair_ptr", "pair_ode", "pair_code", "pair_live", "pair_self", "slot_has_self",
@@ -132,6 +131,25 @@ class DevicePlan:
         self.hidden = np.asarray(hp.slot_state, dtype=np.int64)
 
 
+class LocalProblem:
+    """What one device works on: rows of X, ODE rows (gather tables) and the sweep plan.
+    For a single GPU this is the whole model; ``distributed.localize`` builds the per-rank
+    restriction (owned states first, then halo rows)."""
+
+    def __init__(self, n_rows, n_stats_odes, ode_class, ode_idx, ode_state, host_plan, p):
+        self.n_rows, self.n_stats_odes, self.p = int(n_rows), int(n_stats_odes), int(p)
+        self.ode_class = np.ascontiguousarray(ode_class, dtype=np.int32)
+        self.ode_idx = np.ascontiguousarray(ode_idx, dtype=np.int32)
+        self.ode_state = np.ascontiguousarray(ode_state, dtype=np.int32)
+        self.n_odes = len(self.ode_class)
+        self.host_plan = host_plan
+
+    @classmethod
+    def from_model(cls, model: OdeModel, hidden, couplings=None, schedule="reference"):
+        hp = build_host_plan(model, hidden, couplings=couplings, schedule=schedule)
+        return cls(model.K, model.K, model.ode_class, model.ode_idx, model.ode_state, hp, model.p)
+
+
 class VGMEngine:
     """Mean-field variational gradient matching on one GPU.
 
@@ -146,20 +164,22 @@ class VGMEngine:
 
     def __init__(self, model: OdeModel, D, A=None, hidden=None, couplings=None, schedule="reference",
                  theta_mode="reference", theta_literal=(8.0,), tol=1e-13, max_iter=0, check_every=8,
-                 precondition=True, prefer_builtin=True, device=None):
+                 precondition=True, prefer_builtin=True, device=None, problem=None):
         self.lib = _lib.load()
         self.dev = device or _lib.require_cuda()
         self.model = model
         self.ops = D if isinstance(D, Operators) else Operators(D, A, device=self.dev)
         self.T, self.ld = self.ops.T, self.ops.ld
-        self.K, self.p = model.K, model.p
+        if problem is None:
+            if hidden is None:
+                hidden = np.arange(model.K)
+            problem = LocalProblem.from_model(model, hidden, couplings=couplings, schedule=schedule)
+        self.problem = problem
+        self.K, self.p = problem.n_rows, model.p
         self.program = Program(model, prefer_builtin=prefer_builtin)
-        self.tables = {"ode_class": _i32(model.ode_class, self.dev), "ode_idx": _i32(model.ode_idx, self.dev),
-                       "ode_state": _i32(model.ode_state, self.dev)}
-        if hidden is None:
-            hidden = np.arange(self.K)
-        self.plan = DevicePlan(model, hidden, self.T, self.ld, self.tables, couplings=couplings, schedule=schedule,
-                               device=self.dev)
+        self.tables = {"ode_class": _i32(problem.ode_class, self.dev), "ode_idx": _i32(problem.ode_idx, self.dev),
+                       "ode_state": _i32(problem.ode_state, self.dev)}
+        self.plan = DevicePlan(problem.host_plan, self.T, self.ld, self.tables, device=self.dev)
         if theta_mode not in ("reference", "proxy"):
             raise ValueError("theta_mode must be 'reference' or 'proxy'")
         self.theta_mode = theta_mode
@@ -179,7 +199,7 @@ class VGMEngine:
         if self.plan.c.ruu_const:
             self._cops.M = self.ops.ensure_shared_M(self.plan.c.ruu_value).data_ptr()
         self._mt = _lib.ModelTables()
-        self._mt.n_states, self._mt.n_odes, self._mt.n_param = self.K, self.K, self.p
+        self._mt.n_states, self._mt.n_odes, self._mt.n_param = self.K, problem.n_stats_odes, self.p
         self._mt.ode_class = self.tables["ode_class"].data_ptr()
         self._mt.ode_idx = self.tables["ode_idx"].data_ptr()
         self._mt.ode_state = self.tables["ode_state"].data_ptr()
@@ -256,9 +276,10 @@ class VGMEngine:
 
     def param_stats(self):
         """Sufficient statistics [m | S] of the theta update on the device."""
-        n = self.lib.vgm_param_stats_ws_bytes(self.K, self.T, self.p)
+        n_odes = self.problem.n_stats_odes
+        n = self.lib.vgm_param_stats_ws_bytes(n_odes, self.T, self.p)
         _lib.check(self.lib.vgm_param_stats(self.program.handle, self.X.data_ptr(), self.DX.data_ptr(), self.ld, self.T,
-                                            self.K, self._mt.ode_class, self._mt.ode_idx, self._mt.ode_state,
+                                            n_odes, self._mt.ode_class, self._mt.ode_idx, self._mt.ode_state,
                                             self.stats.data_ptr(), self.ws.data_ptr(), n, _lib.stream_ptr()))
         return self.stats
 
@@ -288,6 +309,24 @@ class VGMEngine:
         _lib.check(rc, allow_notconv=allow_unconverged)
         return self.last_info
 
+    def sweep_prepare(self, theta_star=None):
+        """Phase 1 of a sweep (vgm_state_sweep_prepare)."""
+        self._set_theta_star(theta_star)
+        self._prepare_preconditioner()
+        n = self.lib.vgm_state_sweep_ws_bytes(C.byref(self.plan.c))
+        _lib.check(self.lib.vgm_state_sweep_prepare(self.program.handle, C.byref(self.plan.c), C.byref(self._cops),
+                                                    self.X.data_ptr(), self.DX.data_ptr(), self.theta_star.data_ptr(),
+                                                    self.ws.data_ptr(), n, C.byref(self.info), _lib.stream_ptr()))
+
+    def sweep_level(self, level, allow_unconverged=False):
+        """Phase 2 of a sweep for one dependency level (vgm_state_sweep_level)."""
+        n = self.lib.vgm_state_sweep_ws_bytes(C.byref(self.plan.c))
+        rc = self.lib.vgm_state_sweep_level(C.byref(self.plan.c), C.byref(self._cops), C.byref(self.opts),
+                                            self.X.data_ptr(), int(level), self.ws.data_ptr(), n, C.byref(self.info),
+                                            _lib.stream_ptr())
+        self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
+        _lib.check(rc, allow_notconv=allow_unconverged)
+
     def iteration(self, allow_unconverged=False):
         """theta update followed by the state sweep, all on the device (vgm_iteration_device)."""
         if self._cops.G is None and self.precondition and self.plan.c.ruu_const and self.plan.n_hidden:
@@ -301,16 +340,20 @@ class VGMEngine:
         _lib.check(rc, allow_notconv=allow_unconverged)
         return self.last_info
 
-    def iteration_host(self, X_host_KT: torch.Tensor, theta_host: torch.Tensor, allow_unconverged=False):
+    def iteration_host(self, X_host_KT: torch.Tensor, theta_host: torch.Tensor, X_host_out: torch.Tensor = None,
+                       allow_unconverged=False):
         """End-to-end iteration with HOST buffers (vgm_iteration_host): ``X_host_KT`` is a
-        (pinned) CPU tensor [K, ld], updated in place; ``theta_host`` a CPU tensor [p]."""
+        (pinned) CPU tensor [K, ld]; the updated proxies go to ``X_host_out`` (default: in
+        place); ``theta_host`` a CPU tensor [p]."""
+        if X_host_out is None:
+            X_host_out = X_host_KT
         if self._cops.G is None and self.precondition and self.plan.c.ruu_const and self.plan.n_hidden:
             self.X.copy_(X_host_KT, non_blocking=True)
             self.compute_DX()
             self._prepare_preconditioner()
         rc = self.lib.vgm_iteration_host(self.program.handle, C.byref(self._mt), C.byref(self.plan.c),
                                          C.byref(self._cops), C.byref(self.opts), X_host_KT.data_ptr(),
-                                         theta_host.data_ptr(), self.X.data_ptr(), self.DX.data_ptr(),
+                                         X_host_out.data_ptr(), theta_host.data_ptr(), self.X.data_ptr(), self.DX.data_ptr(),
                                          self.theta.data_ptr(), self.stats.data_ptr(), self.ws.data_ptr(),
                                          self.ws.numel(), C.byref(self.info), _lib.stream_ptr())
         self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
