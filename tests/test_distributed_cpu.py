@@ -76,7 +76,7 @@ def test_localize_reproduces_global_structure(K, world, allhidden):
     assert sorted(seen_slots) == sorted(hidden)
 
 
-def _halo_worker(rank, world, port, K, ret):
+def _halo_worker(rank, world, port, K, outdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -96,15 +96,17 @@ def _halo_worker(rank, world, port, K, ret):
         part = X[:loc.n_owned].sum().reshape(1).clone()
         dist.all_reduce(part)
         ok = ok and abs(part.item() - Xg.sum().item()) < 1e-9
-        ret[rank] = ok
+        with open(os.path.join(outdir, "rank%d.txt" % rank), "w") as f:
+            f.write("ok" if ok else "bad")
     finally:
         dist.destroy_process_group()
 
 
-def test_halo_exchange_and_allreduce_gloo_world2():
+@pytest.mark.timeout(180)
+def test_halo_exchange_and_allreduce_gloo_world2(tmp_path):
     world, K = 2, 16
     port = _free_port()
-    mgr = mp.Manager()
-    ret = mgr.dict()
-    mp.spawn(_halo_worker, args=(world, port, K, ret), nprocs=world, join=True)
-    assert all(ret[r] for r in range(world)) and len(ret) == world
+    # spawn context only (no fork: forking a process that already runs BLAS threads can deadlock)
+    mp.spawn(_halo_worker, args=(world, port, K, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d.txt" % r)).read() == "ok"

@@ -254,19 +254,28 @@ def test_state_cov_vs_oracle(pkg):
     assert relerr(cov, vo.lorenz96_state_cov(g["X0"], 3, g["D"], g["A"])) < TOL
 
 
-def test_colour_schedule_converges_close_to_reference_order(pkg):
-    """Opt-in multi-colour schedule: not the reference's order, so only a loose agreement of the
-    converged proxies is expected (own tolerance, reported separately from parity)."""
+def test_colour_schedule_opt_in(pkg):
+    """Opt-in multi-colour schedule (north_star: reported separately, own tolerance).  It is not
+    the reference's update order, so no 1e-9 parity is claimed; the stated tolerance is on the
+    converged hidden-state RMSE against the ground truth: within 5 % of the reference-order RMSE."""
     p, _lib, engine = pkg
-    g = load("lorenz96_K8_T30_allhidden.npz")
-    model = p.OdeModel.lorenz96(8)
-    a = engine.VGMEngine(model, g["D"], g["A"], hidden=list(range(8)), schedule="reference")
-    b = engine.VGMEngine(model, g["D"], g["A"], hidden=list(range(8)), schedule="colour")
-    a.set_states(g["X0"]); b.set_states(g["X0"])
-    for _ in range(30):
+    from variational_gradient_matching_for_dynamical_systems_b200.synthetic import lorenz96_problem, lorenz96_trajectory
+    K, T = 24, 200
+    t, X0, hidden = lorenz96_problem(K, T, 0.05, seed=5)
+    _, Xtrue = lorenz96_trajectory(K, T, 0.05, seed=5)
+    D, A, *_ = vo.kernel_function(t, t, "rbf", [0.0625, 1.0])
+    model = p.OdeModel.lorenz96(K)
+    a = engine.VGMEngine(model, D, None, hidden=hidden, schedule="reference")
+    b = engine.VGMEngine(model, D, None, hidden=hidden, schedule="colour")
+    a.set_states_state_major(X0); b.set_states_state_major(X0)
+    for _ in range(10):
         a.iteration(); b.iteration()
-    assert b.plan.host.n_levels <= 5 < a.plan.host.n_levels
-    assert relerr(b.get_states(), a.get_states()) < 0.2
+    assert a.plan.host.n_levels == 2 and b.plan.host.n_levels <= 3
+    rm = lambda e: float(((e.X[1::2, :T] - Xtrue[1::2]) ** 2).mean().sqrt().item())
+    r0 = float(((X0[1::2] - Xtrue[1::2]) ** 2).mean().sqrt().item())
+    ra, rb = rm(a), rm(b)
+    assert ra < r0 and rb < r0
+    assert abs(rb - ra) <= 0.05 * ra + 1e-3, (ra, rb)
 
 
 def test_two_rank_state_block_partition_matches_single_gpu():
