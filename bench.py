@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precondition", action="store_true")
+    ap.add_argument("--precond-dtype", default="bf16", choices=["bf16", "f64"])
     return ap.parse_args()
 
 
@@ -175,7 +176,7 @@ def native_arm(args):
     ops = Operators(kf["D"][:, :T], None, device=dev)
     _, X0, hidden = lorenz96_problem(K, T, DT, seed=0, device=dev)        # [K, T] on the device
     model = OdeModel.lorenz96(K)
-    kw = dict(precondition=not args.no_precondition)
+    kw = dict(precondition=not args.no_precondition, precond_dtype=args.precond_dtype)
     if world > 1:
         from variational_gradient_matching_for_dynamical_systems_b200.distributed import DistributedVGMEngine
         eng = DistributedVGMEngine(model, ops, None, hidden=hidden, **kw)
@@ -312,8 +313,8 @@ def native_arm(args):
             "config": {"workload": "Lorenz96 K=%d states (%d hidden, every second state observed+clamped), T=%d; "
                                    "one step = analytical theta update + full state sweep from the same initial "
                                    "proxies" % (K, K_h, T),
-                       "kernel": KERNEL, "dt": DT, "solver": "batched PCG (tol 1e-13) as FP64 DMMA GEMMs" +
-                       ("" if not args.no_precondition else ", no preconditioner"),
+                       "kernel": KERNEL, "dt": DT, "solver": "batched PCG (tol 1e-13): operator as FP64 DMMA GEMM, preconditioner " +
+                       ("none" if args.no_precondition else "(M+shift I)^-1 applied in " + args.precond_dtype),
                        "parallelism": "state-block x%d" % world,
                        "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
                              (n_hidden_local * core.ld * 8 / 1e6)},

@@ -87,6 +87,7 @@ typedef struct {
   int dot_ld;
 } vgm_gemm_args;
 int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream);
+int vgm_dgemm_set_variant(int variant); /* tuning knob: tile configuration of the large-N GEMM (0 = default) */
 int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row of dot_out */
 /* Per-launch CUDA-event timing of the GEMM kernel (used by bench.py for the roofline figure). */
 int vgm_profile_gemm_enable(int on);
@@ -171,7 +172,10 @@ typedef struct {
   const double* DT;  /* its transpose                                   */
   const double* M;   /* (c I - D)^T (c I - D) if plan.ruu_const else null */
   const double* G;   /* optional preconditioner (M + shift I)^-1, else null */
+  const void* G_bf16; /* optional BF16 copy of G (vgm_convert_bf16): if set, the preconditioner is applied on
+                         the BF16 tensor cores with FP32 accumulation instead of the FP64 DMMA pipe */
 } vgm_operators;
+int vgm_convert_bf16(const double* in, void* out_bf16, int rows, int ld, vgm_stream_t stream);
 
 typedef struct {
   double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)  */

@@ -34,7 +34,7 @@ def test_struct_sizes_match_c_layout():
     assert ctypes.sizeof(_lib.GemmArgs) == 3 * 8 + 6 * 4 + 3 * 8 + 2 * 8 + 8 + 3 * 8 + 3 * 8 + 2 * 8 + 8
     assert ctypes.sizeof(_lib.SolverOpts) == 16
     assert ctypes.sizeof(_lib.SweepInfo) == 16
-    assert ctypes.sizeof(_lib.Operators) == 32
+    assert ctypes.sizeof(_lib.Operators) == 40
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -202,6 +202,14 @@ def test_lorenz96_fused_iteration_matches_stepwise(pkg):
         assert relerr(eng.get_states(), g["states"][it]) < TOL
 
 
+def test_lorenz96_fp64_preconditioner_matches_too(pkg):
+    g = load("lorenz96_K12_T100.npz")
+    eng = _engine_from_golden(pkg, g, vo.lorenz96_ode_lines(12), ["_alpha"], precond_dtype="f64")
+    eng.theta_step()
+    eng.state_sweep()
+    assert relerr(eng.get_states(), g["states"][0]) < TOL
+
+
 def test_lorenz96_plain_cg_matches_too(pkg):
     g = load("lorenz96_K12_T100.npz")
     eng = _engine_from_golden(pkg, g, vo.lorenz96_ode_lines(12), ["_alpha"], precondition=False)

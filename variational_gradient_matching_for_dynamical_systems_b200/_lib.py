@@ -55,7 +55,7 @@ class SweepPlan(C.Structure):
 
 
 class Operators(C.Structure):
-    _fields_ = [("D", c_dp), ("DT", c_dp), ("M", c_dp), ("G", c_dp)]
+    _fields_ = [("D", c_dp), ("DT", c_dp), ("M", c_dp), ("G", c_dp), ("G_bf16", c_dp)]
 
 
 class SolverOpts(C.Structure):
@@ -82,8 +82,10 @@ SIGNATURES = {
                                    c_dp, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "vgm_dgemm_nt": (C.c_int, [_P(GemmArgs), C.c_void_p]),
     "vgm_dgemm_dot_tiles": (C.c_int, [C.c_int, C.c_int]),
+    "vgm_dgemm_set_variant": (C.c_int, [C.c_int]),
     "vgm_profile_gemm_enable": (C.c_int, [C.c_int]),
     "vgm_profile_gemm_collect": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
+    "vgm_convert_bf16": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, C.c_void_p]),
     "vgm_transpose": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vgm_gm_operators_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vgm_gm_operators": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_size_t,
@@ -138,6 +140,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    if os.environ.get("VGM_DGEMM_VARIANT"):          # tuning knob, see vgm_dgemm_set_variant
+        lib.vgm_dgemm_set_variant(int(os.environ["VGM_DGEMM_VARIANT"]))
     return lib
 
 

@@ -19,9 +19,9 @@
 
 namespace vgm {
 
-template <int BM_, int BN_, int WARPS_M_, int WARPS_N_>
+template <int BM_, int BN_, int WARPS_M_, int WARPS_N_, int BK_ = 16, int STAGES_ = 4, int MINB_ = 1>
 struct GemmCfg {
-  static constexpr int BM = BM_, BN = BN_, BK = 16, LDS = BK + 4, STAGES = 4;
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, LDS = BK + 4, STAGES = STAGES_, MINB = MINB_;
   static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
   static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
   static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
@@ -31,7 +31,7 @@ struct GemmCfg {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) dgemm_nt_kernel(const vgm_gemm_args a) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const vgm_gemm_args a) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, LDS = Cfg::LDS, STAGES = Cfg::STAGES;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, THREADS = Cfg::THREADS;
   extern __shared__ __align__(16) double smem[];
@@ -216,6 +216,11 @@ static int launch_gemm(const vgm_gemm_args& a, cudaStream_t s) {
 }
 
 using CfgBig = GemmCfg<128, 128, 2, 4>;   // 256 threads, warp tile 64x32
+using CfgV1 = GemmCfg<128, 128, 4, 4>;             // 512 threads, warp tile 32x32
+using CfgV2 = GemmCfg<128, 64, 4, 2, 16, 3, 2>;    // 256 threads, warp tile 32x32, 2 CTAs/SM
+using CfgV3 = GemmCfg<128, 128, 2, 4, 32, 3, 1>;   // BK = 32
+using CfgV4 = GemmCfg<128, 128, 2, 4, 16, 3, 1>;   // default tile, 3 stages
+static int g_variant = 0;
 using CfgMid = GemmCfg<64, 64, 2, 2>;     // 128 threads, warp tile 32x32
 using CfgThin = GemmCfg<16, 64, 1, 4>;    // 128 threads, warp tile 16x16 (few rows: halo / tail solves)
 
@@ -223,7 +228,7 @@ int gemm_dot_tiles(int M, int N) {
   // number of column tiles (= partial dot products per row) the chosen configuration produces
   if (N <= 16) return ceil_div(M, CfgThin::BN);
   if ((long long)ceil_div(N, 128) * ceil_div(M, 128) < 120) return ceil_div(M, CfgMid::BN);
-  return ceil_div(M, CfgBig::BN);
+  return ceil_div(M, g_variant == 2 ? CfgV2::BN : CfgBig::BN);
 }
 
 // ---- optional per-launch CUDA-event profile of the GEMM (bench.py roofline) ----------------
@@ -265,7 +270,13 @@ static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s) {
   if (a.N == 0) return VGM_OK;
   if (a.N <= 16) return launch_gemm<CfgThin>(a, s);
   if ((long long)ceil_div(a.N, 128) * ceil_div(a.M, 128) < 120) return launch_gemm<CfgMid>(a, s);
-  return launch_gemm<CfgBig>(a, s);
+  switch (g_variant) {
+    case 1: return launch_gemm<CfgV1>(a, s);
+    case 2: return launch_gemm<CfgV2>(a, s);
+    case 3: return launch_gemm<CfgV3>(a, s);
+    case 4: return launch_gemm<CfgV4>(a, s);
+    default: return launch_gemm<CfgBig>(a, s);
+  }
 }
 
 }  // namespace vgm
@@ -276,6 +287,12 @@ extern "C" int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream) {
     return VGM_EINVAL;
   }
   return vgm::dgemm_nt(*args, (cudaStream_t)stream);
+}
+
+// Tuning knob (tile configuration of the large-N GEMM); 0 is the default.
+extern "C" int vgm_dgemm_set_variant(int v) {
+  vgm::g_variant = v;
+  return VGM_OK;
 }
 
 extern "C" int vgm_profile_gemm_enable(int on) {

@@ -12,6 +12,8 @@
 // tolerance, and the sequential Gauss-Seidel semantics of the reference (:185 alias, :225 live
 // read) are reproduced by solving dependency levels in order and patching rhs with the freshly
 // updated D x_k between levels.
+#include <cuda_bf16.h>
+
 #include "vgm_common.cuh"
 
 struct vgm_program;
@@ -20,6 +22,21 @@ namespace vgm {
 
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s);
 int gemm_dot_tiles(int M, int N);
+
+struct LpGemmArgs {
+  const __nv_bfloat16* A;
+  const __nv_bfloat16* B;
+  double* C;
+  int lda, ldb, ldc;
+  int N, M, K;
+  const int* rows;
+  const int* n_rows_dev;
+  const double* dotw;
+  double* dot_out;
+  int dot_ld;
+};
+int lp_gemm(const LpGemmArgs& a, cudaStream_t s);
+int lp_gemm_dot_tiles(int M);
 int program_state_assemble(const vgm_program* prog, const vgm_sweep_plan* pl, const double* X, const double* DX0,
                            const double* theta, double* Lambda, double* rhs, double* ruu, double* Ruu, double* Rlive,
                            cudaStream_t s);
@@ -40,7 +57,9 @@ struct CgBuf {
   int *done, *iters;              // [n_hidden]
   int *act[2];                    // ping-pong active lists
   int *n_act;                     // device count (2 ints: [0] current, [1] scratch)
-  int n_tiles;
+  int n_tiles;                    // partial dots per row written by the operator GEMM
+  int n_tiles_z;                  // ... by the preconditioner GEMM
+  __nv_bfloat16* Rb;              // [n_hidden][ld] bf16 copy of R (only with the BF16 preconditioner)
 };
 
 __global__ void cg_gather_x_kernel(const double* __restrict__ X, const int* __restrict__ slot_state,
@@ -74,6 +93,7 @@ __global__ void cg_init_kernel(CgBuf cb, const double* __restrict__ rhs, const d
     const double b = rhs[o + t];
     const double r = b - cb.Q[o + t];
     cb.R[o + t] = r;
+    if (cb.Rb) cb.Rb[o + t] = __double2bfloat16(r);
     if (!precond) cb.P[o + t] = r;
     rr += r * r;
     bb += b * b;
@@ -102,7 +122,7 @@ __global__ void cg_init_precond_kernel(CgBuf cb, const int* __restrict__ act, in
   for (int t = threadIdx.x; t < T; t += blockDim.x) cb.P[o + t] = cb.Z[o + t];
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int j = 0; j < cb.n_tiles; ++j) s += cb.rz_part[(size_t)slot * cb.n_tiles + j];
+    for (int j = 0; j < cb.n_tiles_z; ++j) s += cb.rz_part[(size_t)slot * cb.n_tiles_z + j];
     cb.rz[slot] = s;
   }
 }
@@ -127,6 +147,7 @@ __global__ void cg_update_kernel(CgBuf cb, double* __restrict__ X, const int* __
     x[t] += alpha * p;
     const double r = cb.R[o + t] - alpha * cb.Q[o + t];
     cb.R[o + t] = r;
+    if (cb.Rb) cb.Rb[o + t] = __double2bfloat16(r);
     rr += r * r;
   }
   rr = block_sum(rr, red);
@@ -150,7 +171,7 @@ __global__ void cg_precond_dir_kernel(CgBuf cb, const int* __restrict__ act, int
   if (cb.done[slot]) return;
   const size_t o = (size_t)slot * ld;
   double rz_new = 0.0;
-  for (int j = 0; j < cb.n_tiles; ++j) rz_new += cb.rz_part[(size_t)slot * cb.n_tiles + j];
+  for (int j = 0; j < cb.n_tiles_z; ++j) rz_new += cb.rz_part[(size_t)slot * cb.n_tiles_z + j];
   const double beta = rz_new / cb.rz[slot];
   for (int t = threadIdx.x; t < T; t += blockDim.x) cb.P[o + t] = cb.Z[o + t] + beta * cb.P[o + t];
   __syncthreads();
@@ -241,7 +262,8 @@ static size_t pcg_ws_bytes(int n_hidden, int T, int ld) {
   const int n_tiles = ceil_div(T, 64);  // upper bound over GEMM configurations
   const size_t part = align_up((size_t)n_hidden * n_tiles * sizeof(double), 256);
   const size_t vec = align_up((size_t)n_hidden * sizeof(double), 256);
-  return 5 * mat + 2 * part + 3 * vec + 4 * vec /*done, iters, act x2 (ints fit)*/ + 1024;
+  const size_t half = align_up((size_t)n_hidden * ld * sizeof(__nv_bfloat16), 256);
+  return 5 * mat + half + 2 * part + 3 * vec + 4 * vec /*done, iters, act x2 (ints fit)*/ + 1024;
 }
 
 static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, PcgWs& w) {
@@ -258,6 +280,7 @@ static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, Pcg
   c.Q = (double*)p; p += mat;
   c.Z = (double*)p; p += mat;
   c.W = (double*)p; p += mat;
+  c.Rb = (__nv_bfloat16*)p; p += align_up((size_t)n_hidden * ld * sizeof(__nv_bfloat16), 256);
   c.pq_part = (double*)p; p += part;
   c.rz_part = (double*)p; p += part;
   c.rz = (double*)p; p += vec;
@@ -270,6 +293,7 @@ static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, Pcg
   c.n_act = (int*)p; p += 256;
   w.host_poll_dev = (int*)p; p += 256;
   c.n_tiles = 0;
+  c.n_tiles_z = 0;
   return VGM_OK;
 }
 
@@ -309,6 +333,33 @@ static int apply_operator(const vgm_operators* ops, int ruu_const, const double*
   return VGM_OK;
 }
 
+// Z = R G^T with partial dots r.z -> rz_part (FP64 DMMA, or BF16 tensor cores when G_bf16 is given)
+static int apply_preconditioner(const vgm_operators* ops, CgBuf& cb, const int* act, int n_upper, int T, int ld,
+                                Counters& cnt, cudaStream_t s) {
+  if (ops->G_bf16) {
+    LpGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = cb.Rb; g.B = (const __nv_bfloat16*)ops->G_bf16; g.C = cb.Z;
+    g.lda = g.ldb = g.ldc = ld;
+    g.N = n_upper; g.M = T; g.K = T;
+    g.rows = act; g.n_rows_dev = cb.n_act;
+    g.dotw = cb.R; g.dot_out = cb.rz_part; g.dot_ld = cb.n_tiles_z;
+    VGM_TRY(lp_gemm(g, s));
+  } else {
+    vgm_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.A = cb.R; g.B = ops->G; g.C = cb.Z;
+    g.lda = g.ldb = g.ldc = ld;
+    g.N = n_upper; g.M = T; g.K = T;
+    g.rowsA = act; g.rowsC = act; g.n_rows_dev = cb.n_act;
+    g.alpha = 1.0;
+    g.dotw = cb.R; g.dot_out = cb.rz_part; g.dot_ld = cb.n_tiles_z;
+    VGM_TRY(dgemm_nt(g, s));
+  }
+  cnt.gemm += 1; cnt.launches += 1;
+  return VGM_OK;
+}
+
 static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu, const double* Lambda,
                      const double* rhs, double* X, const int* slot_state, const int* slot_has_self, const int* rows,
                      int n_rows, int T, int ld, const vgm_solver_opts* opts, PcgWs& w, vgm_sweep_info* info,
@@ -320,10 +371,14 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
   const double tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
   const int max_iter = (opts && opts->max_iter > 0) ? opts->max_iter : 4 * T;
   const int check_every = (opts && opts->check_every > 0) ? opts->check_every : 8;
-  const int precond = (ruu_const && ops->G) ? 1 : 0;
+  const int precond = (ruu_const && (ops->G || ops->G_bf16)) ? 1 : 0;
   const double tol2 = tol * tol;
   CgBuf& cb = w.cb;
   cb.n_tiles = gemm_dot_tiles(T, n_rows);
+  const bool lp = precond && ops->G_bf16 != nullptr;
+  cb.n_tiles_z = lp ? lp_gemm_dot_tiles(T) : cb.n_tiles;
+  __nv_bfloat16* const rb_keep = cb.Rb;
+  if (!lp) cb.Rb = nullptr;      // the vector kernels only maintain the bf16 residual when it is used
   const int th = row_threads(T);
 
   VGM_CUDA_OK(cudaMemcpyAsync(cb.act[0], rows, (size_t)n_rows * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -337,18 +392,10 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
   VGM_LAUNCH_OK();
   cnt.launches += 4;
   if (precond) {
-    vgm_gemm_args g;
-    memset(&g, 0, sizeof(g));
-    g.A = cb.R; g.B = ops->G; g.C = cb.Z;
-    g.lda = g.ldb = g.ldc = ld;
-    g.N = n_rows; g.M = T; g.K = T;
-    g.rowsA = act; g.rowsC = act; g.n_rows_dev = cb.n_act;
-    g.alpha = 1.0;
-    g.dotw = cb.R; g.dot_out = cb.rz_part; g.dot_ld = cb.n_tiles;
-    VGM_TRY(dgemm_nt(g, s));
+    VGM_TRY(apply_preconditioner(ops, cb, act, n_rows, T, ld, cnt, s));
     cg_init_precond_kernel<<<n_rows, th, 0, s>>>(cb, act, T, ld);
     VGM_LAUNCH_OK();
-    cnt.gemm += 1; cnt.launches += 2;
+    cnt.launches += 1;
   }
 
   int n_upper = n_rows;  // host-side upper bound of the active count
@@ -362,18 +409,10 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
       VGM_LAUNCH_OK();
       cnt.launches += 1;
       if (precond) {
-        vgm_gemm_args g;
-        memset(&g, 0, sizeof(g));
-        g.A = cb.R; g.B = ops->G; g.C = cb.Z;
-        g.lda = g.ldb = g.ldc = ld;
-        g.N = n_upper; g.M = T; g.K = T;
-        g.rowsA = act; g.rowsC = act; g.n_rows_dev = cb.n_act;
-        g.alpha = 1.0;
-        g.dotw = cb.R; g.dot_out = cb.rz_part; g.dot_ld = cb.n_tiles;
-        VGM_TRY(dgemm_nt(g, s));
+        VGM_TRY(apply_preconditioner(ops, cb, act, n_upper, T, ld, cnt, s));
         cg_precond_dir_kernel<<<n_upper, th, 0, s>>>(cb, act, T, ld);
         VGM_LAUNCH_OK();
-        cnt.gemm += 1; cnt.launches += 2;
+        cnt.launches += 1;
       }
     }
     // drop converged rows, then poll the new count
@@ -388,7 +427,9 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
     n_upper = host_cnt[0];
     // the GEMM tile configuration (hence the number of partial dots per row) follows the host bound
     cb.n_tiles = gemm_dot_tiles(T, n_upper > 0 ? n_upper : 1);
+    if (!lp) cb.n_tiles_z = cb.n_tiles;
   }
+  cb.Rb = rb_keep;
   cg_count_unconverged_kernel<<<1, 256, 0, s>>>(rows, n_rows, cb.done, cb.iters, w.host_poll_dev);
   VGM_LAUNCH_OK();
   int res[2] = {0, 0};

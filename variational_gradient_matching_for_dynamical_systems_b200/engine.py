@@ -48,6 +48,7 @@ class Operators:
         self.M = None
         self.M_c = None
         self.G = None
+        self.G_bf16 = None
         self.G_shift = None
 
     def _pad(self, M):
@@ -88,6 +89,9 @@ class Operators:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
         _lib.check(lib.vgm_spd_inverse(S.data_ptr(), T, ld, G.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr()))
         self.G, self.G_shift = G, float(shift)
+        # BF16 copy for the tensor-core application of the preconditioner
+        self.G_bf16 = torch.zeros((T, ld), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(lib.vgm_convert_bf16(G.data_ptr(), self.G_bf16.data_ptr(), T, ld, _lib.stream_ptr()))
         return G
 
 
@@ -164,7 +168,7 @@ class VGMEngine:
 
     def __init__(self, model: OdeModel, D, A=None, hidden=None, couplings=None, schedule="reference",
                  theta_mode="reference", theta_literal=(8.0,), tol=1e-13, max_iter=0, check_every=8,
-                 precondition=True, prefer_builtin=True, device=None, problem=None):
+                 precondition=True, precond_dtype="bf16", prefer_builtin=True, device=None, problem=None):
         self.lib = _lib.load()
         self.dev = device or _lib.require_cuda()
         self.model = model
@@ -188,6 +192,9 @@ class VGMEngine:
             raise TypeError("the reference plugs the literal [8] into R_uk, r_uk (proxies...py:211); a model with %d "
                             "parameters needs theta_mode='proxy' or a theta_literal of that length" % self.p)
         self.precondition = bool(precondition)
+        if precond_dtype not in ("bf16", "f64"):
+            raise ValueError("precond_dtype must be 'bf16' or 'f64'")
+        self.precond_dtype = precond_dtype
         self.opts = _lib.SolverOpts(tol, max_iter, check_every)
         self.X = torch.zeros((self.K, self.ld), dtype=torch.float64, device=self.dev)
         self.DX = torch.zeros_like(self.X)
@@ -237,6 +244,7 @@ class VGMEngine:
     def _prepare_preconditioner(self):
         if not (self.precondition and self.plan.c.ruu_const) or self.plan.n_hidden == 0:
             self._cops.G = None
+            self._cops.G_bf16 = None
             return
         if self.ops.G is None:
             # shift = mean of Lambda over all hidden states/time points of the current proxy
@@ -255,6 +263,7 @@ class VGMEngine:
                 shift = 1.0
             self.ops.ensure_preconditioner(shift)
         self._cops.G = self.ops.G.data_ptr()
+        self._cops.G_bf16 = self.ops.G_bf16.data_ptr() if self.precond_dtype == "bf16" else None
 
     def _set_theta_star(self, theta_star=None):
         if theta_star is not None:
