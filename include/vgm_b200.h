@@ -87,7 +87,7 @@ typedef struct {
   int dot_ld;
 } vgm_gemm_args;
 int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream);
-int vgm_dgemm_set_variant(int variant); /* tuning knob: tile configuration of the large-N GEMM (0 = default) */
+int vgm_dgemm_set_variant(int variant); /* tuning knob: tile configuration of the large-N GEMM (default 2) */
 int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row of dot_out */
 /* Per-launch CUDA-event timing of the GEMM kernel (used by bench.py for the roofline figure). */
 int vgm_profile_gemm_enable(int on);
