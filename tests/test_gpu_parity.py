@@ -298,3 +298,83 @@ def test_two_rank_state_block_partition_matches_single_gpu():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert '"ok": true' in out.stdout
+
+
+def test_dropin_api_call_sequence_matches_reference_golden(pkg, tmp_path):
+    """The reference's own call sequence (VGM_for_Lotka_Volterra.ipynb cells 25-41) through the
+    drop-in modules, DataFrames in / DataFrames out, against the live reference's output."""
+    import pandas as pd
+    import sympy as sym
+    from variational_gradient_matching_for_dynamical_systems_b200 import GP_regression as GP
+    from variational_gradient_matching_for_dynamical_systems_b200 import import_odes as io_
+    from variational_gradient_matching_for_dynamical_systems_b200 import proxies_for_ode_parameters_and_states as PX
+    from variational_gradient_matching_for_dynamical_systems_b200 import rewrite_odes_as_local_linear_combinations as rw
+    g = load("lorenz96_K10_T40.npz")
+    K = 10
+
+    class symbols:
+        state = sym.symbols(["_x_%d" % (i + 1) for i in range(K)])
+        param = sym.symbols(["_alpha"])
+
+    class locally_linear_odes:
+        class ode_param:
+            B = None
+            b = None
+
+        class state:
+            R = None
+            r = None
+    path = os.path.join(str(tmp_path), "Lorenz96_ODEs.txt")
+    open(path, "w").write("\n".join(vo.lorenz96_ode_lines(K)) + "\n")
+    odes, odes_sym = io_.import_odes(symbols, path)
+    state_couplings, _ = io_.find_state_couplings_in_odes(odes_sym, symbols)
+    t = g["t"]
+    dC_times_inv_C, eps_cov, cov, cov_obs, cov_state_obs = GP.kernel_function(t, t, 'rbf', list(g["kernel_param"]))
+    assert relerr(dC_times_inv_C, g["D"]) < TOL and relerr(eps_cov, g["A"]) < TOL
+    locally_linear_odes.ode_param.B, locally_linear_odes.ode_param.b = \
+        rw.rewrite_odes_as_linear_combination_in_parameters(odes, symbols.state, symbols.param)
+    observed = [str(s) for s in g["observed"]]
+    locally_linear_odes.state.R, locally_linear_odes.state.r = rw.rewrite_odes_as_linear_combination_in_states(
+        odes, symbols.state, symbols.param, sym.symbols(observed), state_couplings)
+    names = [str(s) for s in g["names"]]
+    state = pd.DataFrame(g["X0"], columns=names, index=t).rename_axis("time")
+    observations = pd.DataFrame(g["X0"][:, 0::2], columns=observed, index=t)
+    for it in range(g["thetas"].shape[0]):
+        param = PX.proxy_for_ode_parameters(state, locally_linear_odes, dC_times_inv_C, eps_cov, symbols.param, None,
+                                            odes, None, None, optimizer='analytical')
+        assert list(param.index) == ["_alpha"] and list(param.columns) == ["value"]
+        assert relerr(param.values.ravel(), g["thetas"][it]) < TOL
+        state = PX.proxy_for_ind_states(state, param, odes, None, locally_linear_odes, dC_times_inv_C, eps_cov, None,
+                                        None, observations, None, state_couplings, clamp_states_to_observation_fit=True,
+                                        optimizer='analytical')
+        assert list(state.columns) == names and state.index.name == "time"
+        assert relerr(state.values, g["states"][it]) < TOL
+    with pytest.raises(ValueError, match="wrong shape"):
+        PX.proxy_for_ode_parameters(state.iloc[:5], locally_linear_odes, dC_times_inv_C, eps_cov, symbols.param, None,
+                                    odes, None, None, optimizer='analytical')
+    with pytest.raises(NotImplementedError):
+        PX.proxy_for_ode_parameters(state, locally_linear_odes, dC_times_inv_C, eps_cov, symbols.param, None, odes, None)
+
+
+def test_fitting_state_observations_vs_reference_golden(pkg):
+    import pandas as pd
+    from variational_gradient_matching_for_dynamical_systems_b200 import GP_regression as GP
+    g = load("fitting_state_observations.npz")
+    names = [str(s) for s in g["names"]]
+    obs = pd.DataFrame(g["Y"], index=g["t2"], columns=[names[c] for c in g["obs_cols"]])
+    mean, inv_cov = GP.fitting_state_observations(obs, names, float(g["SNR"]), g["t"], g["C"], g["Cobs"], g["Cso"])
+    assert relerr(mean.values, g["mean"]) < TOL
+    assert list(mean.columns) == names
+
+
+def test_sklearn_compatible_kernels_hit_the_cuda_kernel(pkg):
+    from sklearn.gaussian_process import kernels as sk
+    from variational_gradient_matching_for_dynamical_systems_b200 import kernels as vk
+    X = np.linspace(0, 3, 57)[:, None]
+    Y = np.linspace(0.5, 2, 11)[:, None]
+    assert relerr(vk.RBF(length_scale=0.7)(X), sk.RBF(length_scale=0.7)(X)) < 1e-13
+    assert relerr(vk.RBF(length_scale=0.7)(X, Y), sk.RBF(length_scale=0.7)(X, Y)) < 1e-13
+    a, b = vk.RationalQuadratic(length_scale=1.3, alpha=0.4), sk.RationalQuadratic(length_scale=1.3, alpha=0.4)
+    assert relerr(a(X), b(X)) < 1e-13 and relerr(a(X, Y), b(X, Y)) < 1e-13
+    k = 2.0 * vk.RBF(0.5) + vk.WhiteKernel(0.1)            # operators still compose
+    assert k(X).shape == (57, 57)

@@ -221,7 +221,7 @@ class VGMEngine:
     # ---- data movement ---------------------------------------------------------------------
     def set_states(self, X_TK):
         """Upload a T x K array (reference orientation)."""
-        X = torch.as_tensor(np.asarray(X_TK, dtype=np.float64)) if not torch.is_tensor(X_TK) else X_TK
+        X = torch.from_numpy(np.array(X_TK, dtype=np.float64, copy=True)) if not torch.is_tensor(X_TK) else X_TK
         if X.shape != (self.T, self.K):
             raise ValueError("Either state_proxy or dC_times_invC have the wrong shape")
         self.X.zero_()

@@ -1,0 +1,161 @@
+"""Drop-in for the reference's ``VGM_modules/proxies_for_ode_parameters_and_states.py``:
+the two coordinate-ascent updates with their verbatim signatures, computed on the GPU.
+
+* ``proxy_for_ode_parameters``  <- proxies_for_ode_parameters_and_states.py:41-139
+* ``proxy_for_ind_states``      <- proxies_for_ode_parameters_and_states.py:159-375
+
+Scope: ``optimizer='analytical'`` -- the closed-form Gaussian updates.
+``optimizer='minimizer'`` (SciPy BFGS on a squared loss) is third-party arithmetic outside the
+B200 path and raises ``NotImplementedError``.  Plotting side effects are omitted.
+
+Reference behaviours that are reproduced on purpose:
+
+* the state update evaluates R_uk, r_uk on a snapshot of the proxies taken once per sweep but
+  reads ``D x_k`` from the live, already updated columns (:185,:191,:225);
+* the state update ignores the estimated ODE parameters and plugs in the literal ``[8]``
+  (:211).  ``settings.theta_mode = 'reference'`` (default) does the same for one-parameter
+  models; for models with several parameters the shipped reference raises ``TypeError``, so
+  the passed ``ode_param_proxy`` is used there (what the one-line-patched reference does) and
+  a warning is issued once.  ``settings.theta_mode = 'proxy'`` always uses ``ode_param_proxy``;
+* if state u does not occur in its own ODE the diagonal is doubled (:201,:245).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from .engine import Operators, VGMEngine
+
+
+class settings:
+    """Module-level switches (the reference's signatures have no room for them)."""
+    theta_mode = "reference"        # 'reference' | 'proxy'
+    theta_literal = 8.0             # proxies...py:211
+    tol = 1e-13                     # relative residual of the per-state solves
+    precond_dtype = "bf16"
+    schedule = "reference"          # 'reference' | 'colour' (opt-in parallel multi-colour schedule)
+    _warned = False
+
+
+_engines = {}
+
+
+def _fingerprint(M):
+    M = np.asarray(M)
+    return (M.shape, float(M[0, 0]), float(M[-1, -1]), float(M.sum()), float(M[::7, ::13].sum()))
+
+
+def _model_of(locally_linear_odes):
+    for holder in (getattr(locally_linear_odes, "ode_param", None), getattr(locally_linear_odes, "state", None)):
+        for name in ("B", "b", "R", "r"):
+            obj = getattr(holder, name, None) if holder is not None else None
+            if obj is not None and hasattr(obj, "model"):
+                return obj.model
+    raise TypeError("locally_linear_odes must hold the objects returned by this package's "
+                    "rewrite_odes_as_linear_combination_in_parameters / _in_states")
+
+
+def _engine(model, D, A, hidden, couplings, theta_mode):
+    key = (id(model), _fingerprint(D), tuple(hidden), None if couplings is None else id(couplings), theta_mode,
+           settings.tol, settings.precond_dtype, settings.schedule)
+    eng = _engines.get(key)
+    if eng is None:
+        if len(_engines) > 8:
+            _engines.clear()
+        ops = Operators(D, A)
+        literal = tuple([float(settings.theta_literal)] * model.p)
+        eng = VGMEngine(model, ops, None, hidden=hidden, couplings=couplings, theta_mode=theta_mode,
+                        theta_literal=literal, tol=settings.tol, precond_dtype=settings.precond_dtype,
+                        schedule=settings.schedule)
+        _engines[key] = eng
+    return eng
+
+
+def proxy_for_ode_parameters(state_proxy, locally_linear_odes, dC_times_inv_C, eps_cov, ode_param_symbols,
+                             ode_param_true, odes, odes_gradient, constraints=None, optimizer='minimizer',
+                             fig_shape=(7, 4), init=None):
+    '''Estimates proxy for ODE parameters'''
+    # error handling, proxies...py:47-50
+    if state_proxy.shape[0] != dC_times_inv_C.shape[0]:
+        raise ValueError('Either state_proxy or dC_times_invC have the wrong shape')
+    elif dC_times_inv_C.shape[0] != dC_times_inv_C.shape[1]:
+        raise ValueError('dC_times_invC is not a square matrix')
+    if optimizer != 'analytical':
+        raise NotImplementedError("optimizer=%r: only the closed-form 'analytical' update runs on the B200 path "
+                                  "(the SciPy 'minimizer' branch, proxies...py:114-128, is out of scope)" % (optimizer,))
+    model = _model_of(locally_linear_odes)
+    fp = _fingerprint(dC_times_inv_C)
+    eng = next((e for k, e in _engines.items() if k[0] == id(model) and k[1] == fp), None)   # reuse the sweep engine
+    if eng is None:
+        eng = _engine(model, dC_times_inv_C, None, (), None, "proxy")
+    eng.set_states(np.asarray(state_proxy.values, dtype=np.float64))
+    eng.compute_DX()
+    stats = eng.param_stats().cpu().numpy()
+    p = model.p
+    local_mean, local_scaling = stats[:p], stats[p:].reshape(p, p)
+    if constraints is None:
+        global_mean = eng.param_solve()[:p].cpu().numpy()            # proxies...py:93
+    else:
+        # the constrained variants are scikit-learn fits on the p x p normal equations (:97-109)
+        from sklearn.linear_model import Lasso, Ridge
+        if constraints == 'nonnegative':
+            reg = Lasso(alpha=0.00001, positive=True)
+        elif constraints == 'shrinkage':
+            reg = Ridge(alpha=1)
+        elif constraints == 'sparse':
+            reg = Lasso(alpha=1)
+        elif constraints == 'sparse+nonnegative':
+            reg = Lasso(alpha=1, positive=True)
+        else:
+            raise ValueError("unknown constraints %r" % (constraints,))
+        global_mean = reg.fit(local_scaling, np.squeeze(local_mean)).coef_
+    return pd.DataFrame(global_mean, columns=['value'], index=map(str, ode_param_symbols)).rename_axis(
+        'ODE parameter symbols')
+
+
+def proxy_for_ind_states(state_proxy, ode_param_proxy, odes, odes_gradient_states, locally_linear_odes,
+                         dC_times_inv_C, eps_cov, state_pred_mean, state_pred_inv_cov, observations, true_states,
+                         state_couplings, burnin=5, clamp_states_to_observation_fit=True, constraints=None,
+                         optimizer='analytical', fig_shape=(10, 8)):
+    '''Estimates proxy for each individual state'''
+    if optimizer != 'analytical':
+        raise NotImplementedError("optimizer=%r: only the closed-form 'analytical' sweep runs on the B200 path "
+                                  "(proxies...py:278-366 is SciPy L-BFGS-B, out of scope)" % (optimizer,))
+    if constraints is not None:
+        raise NotImplementedError("constraints=%r: the scikit-learn Lasso branch (proxies...py:270-272) is out of "
+                                  "scope" % (constraints,))
+    time_points = np.array(state_proxy.index)
+    state_symbols = state_proxy.columns.values
+    X = np.asarray(state_proxy.values, dtype=np.float64)
+    model = _model_of(locally_linear_odes)
+    if clamp_states_to_observation_fit == True:  # noqa: E712  (same test as proxies...py:175)
+        obs_cols = set(observations.columns.values)
+        hidden = [u for u in range(len(state_symbols)) if state_symbols[u] not in obs_cols]
+    else:
+        hidden = list(range(len(state_symbols)))
+    theta = np.asarray(getattr(ode_param_proxy, "values", ode_param_proxy), dtype=np.float64).ravel()
+    theta_mode = settings.theta_mode
+    if theta_mode == "reference" and model.p != 1:
+        if not settings._warned:
+            warnings.warn("the reference plugs the literal [8] into the state update (proxies...py:211) and raises "
+                          "TypeError for models with %d parameters; using ode_param_proxy instead" % model.p)
+            settings._warned = True
+        theta_mode = "proxy"
+    own = getattr(state_couplings, "_ptr", None) is not None
+    couplings = None if own else state_couplings
+    eng = _engine(model, dC_times_inv_C, None, tuple(hidden), couplings, theta_mode)
+    eng.set_states(X)
+    eng.compute_DX()
+    eng.state_sweep(theta_star=None if theta_mode == "reference" else theta)
+    global_mean = eng.get_states()
+    return pd.DataFrame(global_mean, columns=map(str, state_symbols), index=time_points).rename_axis('time')
+
+
+def _minimizer_only(*_a, **_k):
+    raise NotImplementedError("squared_loss* belong to the SciPy 'minimizer' path (proxies...py:379-434), which is out "
+                              "of scope of the B200 hot path")
+
+
+squared_loss = squared_loss_gradient = squared_loss_states = squared_loss_states_gradient = _minimizer_only
