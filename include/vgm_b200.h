@@ -176,6 +176,11 @@ typedef struct {
                          the BF16 tensor cores with FP32 accumulation instead of the FP64 DMMA pipe */
 } vgm_operators;
 int vgm_convert_bf16(const double* in, void* out_bf16, int rows, int ld, vgm_stream_t stream);
+/* tcgen05/TMEM/TMA BF16 GEMM (FP32 accumulate): Z[rows[j]][m] = sum_k A[j][k] B[m][k] for j < n_rows, with optional
+ * per-row partial dots (one per 256-column tile).  A is a compact [a_rows][lda] bf16 array. */
+int vgm_tc_gemm_bf16(const void* A_bf16, int a_rows, int lda, const void* B_bf16, int M, int K, int ldb, int n_rows,
+                     const int* n_rows_dev, const int* rows, double* Z, int ldz, const double* dotw, double* dot_out,
+                     int dot_ld, vgm_stream_t stream);
 
 typedef struct {
   double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)  */

@@ -86,6 +86,8 @@ SIGNATURES = {
     "vgm_profile_gemm_enable": (C.c_int, [C.c_int]),
     "vgm_profile_gemm_collect": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
     "vgm_convert_bf16": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, C.c_void_p]),
+    "vgm_tc_gemm_bf16": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_dp,
+                                   C.c_int, c_dp, c_dp, C.c_int, C.c_void_p]),
     "vgm_transpose": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vgm_gm_operators_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vgm_gm_operators": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_size_t,
