@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precondition", action="store_true")
-    ap.add_argument("--precond-dtype", default="bf16", choices=["bf16", "f64"])
+    ap.add_argument("--solver", default="auto", choices=["auto", "mixed", "pcg"])
+    ap.add_argument("--inner-iters", type=int, default=10)
+    ap.add_argument("--tol", type=float, default=1e-13)
+    ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel CUDA events in the timed region")
     return ap.parse_args()
 
 
@@ -176,7 +179,7 @@ def native_arm(args):
     ops = Operators(kf["D"][:, :T], None, device=dev)
     _, X0, hidden = lorenz96_problem(K, T, DT, seed=0, device=dev)        # [K, T] on the device
     model = OdeModel.lorenz96(K)
-    kw = dict(precondition=not args.no_precondition, precond_dtype=args.precond_dtype)
+    kw = dict(precondition=not args.no_precondition, solver=args.solver, inner_iters=args.inner_iters, tol=args.tol)
     if world > 1:
         from variational_gradient_matching_for_dynamical_systems_b200.distributed import DistributedVGMEngine
         eng = DistributedVGMEngine(model, ops, None, hidden=hidden, **kw)
@@ -209,7 +212,7 @@ def native_arm(args):
     # ---- timed region: device-resident ------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    lib.vgm_profile_gemm_enable(1)
+    lib.vgm_profile_enable(0 if args.no_profile else 1)
     barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,9 +227,12 @@ def native_arm(args):
     torch.cuda.synchronize()
     barrier()
     ms = e0.elapsed_time(e1)
-    flops, gemm_ms, gemm_n = C.c_double(), C.c_double(), C.c_longlong()
-    lib.vgm_profile_gemm_collect(C.byref(flops), C.byref(gemm_ms), C.byref(gemm_n))
-    lib.vgm_profile_gemm_enable(0)
+    fam = {}
+    for fid, name in enumerate(("dgemm", "tcgemm", "vec", "assemble")):
+        fl, by, fms, fn = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
+        lib.vgm_profile_collect(fid, C.byref(fl), C.byref(by), C.byref(fms), C.byref(fn))
+        fam[name] = {"flops": fl.value, "bytes": by.value, "ms": fms.value, "launches": fn.value}
+    lib.vgm_profile_enable(0)
     clocks = sampler.stop()
     if world > 1:
         tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -279,26 +285,45 @@ def native_arm(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (FP64 DMMA GEMM) ---------------------------------------------
+    # ---- roofline: every kernel family, the dominant one (largest share of the step) on top -------------
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
     except Exception:  # noqa: BLE001
         pass
-    fp64_peak = None
     try:
         with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
             fp64_peak = json.load(f)["cublas_dgemm_8192_tflops"]
     except Exception:  # noqa: BLE001
         fp64_peak = 35.4
-    achieved = flops.value / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value > 0 else None
-    roofline = {"bound": "tensor", "kernel": "vgm::dgemm_nt_kernel (FP64 DMMA)", "achieved": achieved,
-                "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved else None,
-                "traffic": None, "launches": gemm_n.value, "kernel_ms_per_step": gemm_ms.value / args.steps,
-                "share_of_step": gemm_ms.value / ms,
-                "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/fp64_peak.json); "
-                               "MEASURED_PEAKS.json has no FP64 entry (hbm_gbs=%s)" % peaks.get("hbm_gbs")}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)                   # fallback: B200_PROFILING.md
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)    # kernels timed inside a long step
+    peak_src = ("MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md") + \
+               "; FP64: cuBLAS DGEMM 8192^3 measured on this pool (profiles/fp64_peak.json)"
+    names = {"dgemm": "vgm::dgemm_nt_kernel (FP64 DMMA, banded)", "tcgemm": "vgm::tc_gemm_kernel (tcgen05 bf16-split, banded)",
+             "vec": "vgm::ir_update/ir_dir/... (solver vector kernels)", "assemble": "coefficient assembly + theta statistics"}
+    kernels = {}
+    for name, f in fam.items():
+        if f["ms"] <= 0:
+            continue
+        sec = f["ms"] * 1e-3
+        tf, gbs = f["flops"] / sec / 1e12, f["bytes"] / sec / 1e9
+        fpeak = fp64_peak if name == "dgemm" else bf16_peak
+        frac_t, frac_h = (tf / fpeak if f["flops"] else 0.0), gbs / hbm_peak
+        tensor_bound = frac_t >= frac_h
+        kernels[name] = {"kernel": names[name], "bound": "tensor" if tensor_bound else "hbm",
+                         "achieved": tf if tensor_bound else gbs, "peak": fpeak if tensor_bound else hbm_peak,
+                         "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": frac_t if tensor_bound else frac_h,
+                         "tflops": tf, "gbs": gbs, "launches": f["launches"], "ms_per_step": f["ms"] / args.steps,
+                         "share_of_step": f["ms"] / ms}
+    roofline = None
+    if kernels:
+        top = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+        roofline = dict(kernels[top])
+        roofline["traffic"] = None
+        roofline["peak_source"] = peak_src
+        roofline["all_families"] = kernels
     K_h = n_hidden_total
     F_canon = 2.0 * T * T * K + 2.0 * T * T * K_h + K_h * (T ** 3 / 3.0 + 2.0 * T * T) + 40.0 * T * K
     cpu = None
@@ -313,16 +338,22 @@ def native_arm(args):
             "config": {"workload": "Lorenz96 K=%d states (%d hidden, every second state observed+clamped), T=%d; "
                                    "one step = analytical theta update + full state sweep from the same initial "
                                    "proxies" % (K, K_h, T),
-                       "kernel": KERNEL, "dt": DT, "solver": "batched PCG (tol 1e-13): operator as FP64 DMMA GEMM, preconditioner " +
-                       ("none" if args.no_precondition else "(M+shift I)^-1 applied in " + args.precond_dtype),
+                       "kernel": KERNEL, "dt": DT,
+                       "solver": ("mixed precision (tol %g): FP64 residuals on the DMMA pipe, FP32 PCG corrections "
+                                  "(%d steps each) with bf16-split tcgen05 operator products" % (args.tol, args.inner_iters))
+                       if core.solver == "mixed" else
+                       ("FP64 PCG (tol %g) on the DMMA pipe, preconditioner %s" %
+                        (args.tol, "none" if args.no_precondition else "(M+shift I)^-1")),
+                       "bands": {"D": core.ops.band_D, "M": core.ops.band_M, "G_bf16": core.ops.band_G},
                        "parallelism": "state-block x%d" % world,
                        "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
-                             (n_hidden_local * core.ld * 8 / 1e6)},
+                             (n_hidden_local * core.ld * 8 / 1e6),
+                       "profiled": not args.no_profile},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "pcg_iterations": pcg_iters, "theta": theta, "setup_s": setup_s,
+            "solver_iterations": pcg_iters, "theta": theta, "setup_s": setup_s,
             "canonical_flops": {"per_step": F_canon, "tflops": F_canon * args.steps / (ms * 1e-3) / 1e12,
                                 "note": "F of SURVEY.md 8(d) (dense Cholesky per state); the executed algorithm is "
-                                        "PCG, see roofline for executed GEMM flops"}}
+                                        "iterative on banded operators, see roofline for executed work"}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -62,8 +62,11 @@ int vgm_kernel_build(int kernel_type, const double* param_host, int n_param,
  * Epilogue: C = alpha*acc + beta*C0 + g1*(U1 ? U1 : 1).V1 + g2*(U2 ? U2 : 1).V2 (elementwise,
  * operands laid out like C); optional per-row partial dot products
  * dot_out[row*dot_ld + column_tile] = sum_{m in tile} dotw[row][m] * C[row][m].
+ * dotw == C requests the squared row norms of the result.
  * rowsA / rowsC (optional) map logical row n to a physical row of A / of C and of every
  * epilogue operand; n_rows_dev (optional) is a device-side row count (<= N).
+ * band > 0 declares B banded: B[m][k] is treated as zero for |m - k| > band and the k range outside
+ * the band is skipped (vgm_band_halfwidth measures it; band <= 0 means dense).
  */
 typedef struct {
   const double* A;
@@ -85,13 +88,21 @@ typedef struct {
   const double* dotw;
   double* dot_out;
   int dot_ld;
+  int band;
 } vgm_gemm_args;
 int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream);
 int vgm_dgemm_set_variant(int variant); /* tuning knob: tile configuration of the large-N GEMM (default 2) */
 int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row of dot_out */
-/* Per-launch CUDA-event timing of the GEMM kernel (used by bench.py for the roofline figure). */
-int vgm_profile_gemm_enable(int on);
-int vgm_profile_gemm_collect(double* flops, double* ms, long long* launches); /* synchronises the device */
+/* Smallest b such that |B[i][j]| <= rel_threshold * max|B| whenever |i - j| > b (synchronises the stream).
+ * With rel_threshold = 2^-64 the dropped part of any product is below half an ulp of the kept part's
+ * normwise rounding error, i.e. the banded GEMM is FP64-exact in the backward sense. */
+int vgm_band_halfwidth(const double* B, int rows, int cols, int ld, double rel_threshold, int* band_host,
+                       vgm_stream_t stream);
+/* Per-launch CUDA-event timing of the kernel families (used by bench.py for the roofline figures):
+ * family 0 = FP64 DMMA GEMM, 1 = tcgen05 BF16 GEMM, 2 = solver vector kernels, 3 = coefficient assembly. */
+enum { VGM_PROF_DGEMM = 0, VGM_PROF_TCGEMM = 1, VGM_PROF_VEC = 2, VGM_PROF_ASSEMBLE = 3 };
+int vgm_profile_enable(int on);
+int vgm_profile_collect(int family, double* flops, double* bytes, double* ms, long long* launches); /* synchronises */
 int vgm_transpose(const double* in, int ld_in, double* out, int ld_out, int rows, int cols, vgm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
@@ -172,20 +183,28 @@ typedef struct {
   const double* DT;  /* its transpose                                   */
   const double* M;   /* (c I - D)^T (c I - D) if plan.ruu_const else null */
   const double* G;   /* optional preconditioner (M + shift I)^-1, else null */
-  const void* G_bf16; /* optional BF16 copy of G (vgm_convert_bf16): if set, the preconditioner is applied on
-                         the BF16 tensor cores with FP32 accumulation instead of the FP64 DMMA pipe */
+  const void* G_bf16;   /* optional BF16 copy of G (vgm_convert_bf16), [T][ld]                                  */
+  const void* M_bf16x2; /* optional BF16 split of M (vgm_split_bf16), [2][T][ld]: hi = bf16(M), lo = bf16(M - hi).
+                           With G_bf16 it enables the mixed-precision solver: FP64 residuals on the DMMA pipe,
+                           corrections by FP32 PCG whose operator products run on the tcgen05 tensor cores  */
+  double G_shift;       /* the shift G was built with                                                          */
+  double precond_c;     /* > 0: the preconditioner is S G S with S = diag sqrt((G_shift + c) / (Lambda + c))    */
+  int band_D, band_M, band_G; /* half band widths of D (and D^T), M and G (vgm_band_halfwidth); <= 0: dense     */
 } vgm_operators;
 int vgm_convert_bf16(const double* in, void* out_bf16, int rows, int ld, vgm_stream_t stream);
-/* tcgen05/TMEM/TMA BF16 GEMM (FP32 accumulate): Z[rows[j]][m] = sum_k A[j][k] B[m][k] for j < n_rows, with optional
- * per-row partial dots (one per 256-column tile).  A is a compact [a_rows][lda] bf16 array. */
-int vgm_tc_gemm_bf16(const void* A_bf16, int a_rows, int lda, const void* B_bf16, int M, int K, int ldb, int n_rows,
-                     const int* n_rows_dev, const int* rows, double* Z, int ldz, const double* dotw, double* dot_out,
-                     int dot_ld, vgm_stream_t stream);
+int vgm_split_bf16(const double* in, void* out_bf16x2, int rows, int ld, vgm_stream_t stream);
+/* tcgen05/TMEM/TMA BF16 GEMM (FP32 accumulation in tensor memory), raw FP32 output:
+ *   out[j][m] = sum_k A0[j][k] B0[m][k]  (+ A1[j][k] B0[m][k] + A0[j][k] B1[m][k]  if A1 and B1 are given:
+ *   the three leading terms of the product of two bf16-split operands, ~2^-16 relative accuracy).
+ * A*: [n_rows][lda] bf16, B*: [M][ldb] bf16, out: [n_rows][ldo] fp32; band as in vgm_gemm_args. */
+int vgm_tc_gemm_bf16(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1, int M, int K,
+                     int ldb, int band, float* out, int ldo, vgm_stream_t stream);
 
 typedef struct {
-  double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)  */
-  int max_iter;      /* default 4 T                                                        */
-  int check_every;   /* host polls the device-side active count every this many iterations */
+  double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)                     */
+  int max_iter;      /* FP64 PCG: iteration cap (default 4 T); mixed precision: cap on outer corrections (default 30) */
+  int check_every;   /* FP64 PCG: host polls the device-side active count every this many iterations         */
+  int inner_iters;   /* mixed precision: FP32 PCG steps per correction (default 10)                           */
 } vgm_solver_opts;
 
 typedef struct {

@@ -28,13 +28,27 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().vgm_version() >= 100
 
 
-def test_struct_sizes_match_c_layout():
-    """Field offsets of the ctypes mirrors follow the C structs (natural alignment, x86-64)."""
+def test_struct_sizes_match_c_layout(tmp_path):
+    """The ctypes mirrors have the layout gcc gives the C structs of include/vgm_b200.h."""
+    import subprocess
     from variational_gradient_matching_for_dynamical_systems_b200 import _lib
-    assert ctypes.sizeof(_lib.GemmArgs) == 3 * 8 + 6 * 4 + 3 * 8 + 2 * 8 + 8 + 3 * 8 + 3 * 8 + 2 * 8 + 8
-    assert ctypes.sizeof(_lib.SolverOpts) == 16
-    assert ctypes.sizeof(_lib.SweepInfo) == 16
-    assert ctypes.sizeof(_lib.Operators) == 40
+    pairs = {"vgm_gemm_args": _lib.GemmArgs, "vgm_solver_opts": _lib.SolverOpts, "vgm_sweep_info": _lib.SweepInfo,
+             "vgm_operators": _lib.Operators, "vgm_sweep_plan": _lib.SweepPlan, "vgm_model_tables": _lib.ModelTables}
+    lines = []
+    for cname, ct in pairs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vgm_b200.h"\nint main(void){%s return 0;}\n'
+                   % "".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in pairs.items():
+        assert int(out[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -101,6 +101,103 @@ def test_dgemm_epilogue_gather_and_dots(pkg):
     assert (dots[rc].sum(1) - dref).abs().max().item() / dref.abs().max().item() < 1e-12
 
 
+def _banded(T, band, gen, scale=1.0):
+    """Random T x T operator that is exactly zero outside |i - j| <= band."""
+    B = torch.randn((T, T), generator=gen, dtype=torch.float64, device="cuda") * scale
+    i = torch.arange(T, device="cuda")
+    B[(i[:, None] - i[None, :]).abs() > band] = 0.0
+    return B
+
+
+@pytest.mark.parametrize("T,band", [(1000, 146), (333, 40), (130, 7)])
+def test_banded_dgemm_is_exact_and_band_probe_finds_the_band(pkg, T, band):
+    """A banded operator gives the same product with the k range outside the band skipped (bit-for-bit the
+    same partial sums up to FP64 summation order: compare to 1e-14), and vgm_band_halfwidth recovers the band."""
+    _, _lib, _ = pkg
+    gen = torch.Generator(device="cuda").manual_seed(T)
+    ld = (T + 7) // 8 * 8
+    B = torch.zeros((T, ld), dtype=torch.float64, device="cuda")
+    B[:, :T] = _banded(T, band, gen)
+    B[:, :T] += 1e-30 * torch.randn((T, T), generator=gen, dtype=torch.float64, device="cuda")   # numerically zero tail
+    A = torch.zeros((777, ld), dtype=torch.float64, device="cuda")
+    A[:, :T] = torch.randn((777, T), generator=gen, dtype=torch.float64, device="cuda")
+    out = C.c_int(-1)
+    _lib.check(_lib.load().vgm_band_halfwidth(B.data_ptr(), T, T, ld, 2.0 ** -64, C.byref(out), None))
+    assert out.value == band
+    lib, g, Cm = _gemm(_lib, A, B, K=T)
+    g.band = band
+    _lib.check(lib.vgm_dgemm_nt(C.byref(g), None))
+    ref = A[:, :T] @ B[:, :T].t()
+    assert relerr(Cm[:, :T].cpu().numpy(), ref.cpu().numpy()) < 1e-14
+
+
+def _bf16_split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.to(x.dtype)).to(torch.bfloat16)
+    return hi, lo
+
+
+@pytest.mark.parametrize("n,T,band", [(50000, 1000, 146), (300, 1000, 0), (129, 200, 30), (5, 100, 0), (1, 64, 0)])
+@pytest.mark.parametrize("split", [False, True])
+def test_tcgen05_gemm_matches_fp32_reference(pkg, n, T, band, split):
+    """tcgen05 BF16 GEMM (FP32 accumulation in TMEM) against a torch fp64 product of the SAME bf16
+    operands: single pass ~1e-6 (fp32 accumulation), and the bf16-split form reproduces the fp64
+    product of the unsplit fp32 inputs to ~2^-16 (tolerance 1e-4 relative to the row scale)."""
+    _, _lib, _ = pkg
+    lib = _lib.load()
+    gen = torch.Generator(device="cuda").manual_seed(n + T)
+    ld = (T + 7) // 8 * 8
+    P = torch.randn((n, T), generator=gen, dtype=torch.float32, device="cuda")
+    Bm = _banded(T, band, gen).float() if band else torch.randn((T, T), generator=gen, dtype=torch.float32, device="cuda")
+    Phi, Plo = _bf16_split(P)
+    Bhi, Blo = _bf16_split(Bm)
+
+    def padded(x, rows):
+        o = torch.full((rows, ld), float("nan"), dtype=torch.bfloat16, device="cuda")   # pad must never be read
+        o[:, :T] = x
+        return o
+    a0, a1, b0, b1 = padded(Phi, n), padded(Plo, n), padded(Bhi, T), padded(Blo, T)
+    out = torch.full((n, ld), 777.0, dtype=torch.float32, device="cuda")
+    _lib.check(lib.vgm_tc_gemm_bf16(a0.data_ptr(), a1.data_ptr() if split else None, n, ld, b0.data_ptr(),
+                                    b1.data_ptr() if split else None, T, T, ld, band, out.data_ptr(), ld, None))
+    torch.cuda.synchronize()
+    assert bool((out[:, T:] == 777.0).all()), "row padding was written"
+    d = lambda x: x.double()
+    if split:
+        ref_ops = d(Phi) @ d(Bhi).t() + d(Plo) @ d(Bhi).t() + d(Phi) @ d(Blo).t()
+    else:
+        ref_ops = d(Phi) @ d(Bhi).t()
+    scale = float(ref_ops.abs().max())
+    assert float((d(out[:, :T]) - ref_ops).abs().max()) / scale < 2e-6
+    if split:
+        exact = d(P) @ d(Bm).t()
+        assert float((d(out[:, :T]) - exact).abs().max()) / scale < 1e-4
+
+
+def test_mixed_precision_solver_matches_fp64_pcg_and_oracle(pkg):
+    """Lorenz96 K=64, T=256: the mixed-precision solver (tcgen05 corrections, FP64 residuals), FP64 PCG and
+    the oracle's dense LAPACK solves agree to 1e-9; the mixed solver needs only a handful of FP64 GEMMs."""
+    p, _lib, engine = pkg
+    K, T = 64, 256
+    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=5)
+    rng = np.random.default_rng(6)
+    X0 = Xtrue.copy()
+    X0[:, 1::2] += 0.5 * rng.standard_normal((T, K // 2))
+    D, A, *_ = vo.kernel_function(t, t, "rbf", [0.0625, 1.0])
+    hidden = list(range(1, K, 2))
+    Xref = vo.lorenz96_state_sweep(X0, 8.0, D, hidden)
+    res = {}
+    for solver in ("mixed", "pcg"):
+        eng = engine.VGMEngine(p.OdeModel.lorenz96(K), D, A, hidden=hidden, solver=solver)
+        assert eng.solver == solver
+        eng.set_states(X0)
+        eng.iteration()
+        res[solver] = (eng.get_states(), dict(eng.last_info))
+        assert relerr(res[solver][0], Xref) < TOL, (solver, eng.last_info)
+        assert eng.last_info["unconverged"] == 0
+    assert relerr(res["mixed"][0], res["pcg"][0]) < 1e-10
+
+
 def _kernel_function_gpu(_lib, t, t2, ktype, kparam):
     lib = _lib.load()
     T, T2 = len(t), len(t2)
@@ -204,7 +301,7 @@ def test_lorenz96_fused_iteration_matches_stepwise(pkg):
 
 def test_lorenz96_fp64_preconditioner_matches_too(pkg):
     g = load("lorenz96_K12_T100.npz")
-    eng = _engine_from_golden(pkg, g, vo.lorenz96_ode_lines(12), ["_alpha"], precond_dtype="f64")
+    eng = _engine_from_golden(pkg, g, vo.lorenz96_ode_lines(12), ["_alpha"], solver="pcg")
     eng.theta_step()
     eng.state_sweep()
     assert relerr(eng.get_states(), g["states"][0]) < TOL

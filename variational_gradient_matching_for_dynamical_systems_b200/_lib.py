@@ -39,7 +39,7 @@ class GemmArgs(C.Structure):
                 ("alpha", C.c_double), ("beta", C.c_double), ("C0", c_dp),
                 ("U1", c_dp), ("V1", c_dp), ("g1", C.c_double),
                 ("U2", c_dp), ("V2", c_dp), ("g2", C.c_double),
-                ("dotw", c_dp), ("dot_out", c_dp), ("dot_ld", C.c_int)]
+                ("dotw", c_dp), ("dot_out", c_dp), ("dot_ld", C.c_int), ("band", C.c_int)]
 
 
 class SweepPlan(C.Structure):
@@ -55,11 +55,13 @@ class SweepPlan(C.Structure):
 
 
 class Operators(C.Structure):
-    _fields_ = [("D", c_dp), ("DT", c_dp), ("M", c_dp), ("G", c_dp), ("G_bf16", c_dp)]
+    _fields_ = [("D", c_dp), ("DT", c_dp), ("M", c_dp), ("G", c_dp), ("G_bf16", c_dp), ("M_bf16x2", c_dp),
+                ("G_shift", C.c_double), ("precond_c", C.c_double),
+                ("band_D", C.c_int), ("band_M", C.c_int), ("band_G", C.c_int)]
 
 
 class SolverOpts(C.Structure):
-    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("check_every", C.c_int)]
+    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("check_every", C.c_int), ("inner_iters", C.c_int)]
 
 
 class SweepInfo(C.Structure):
@@ -83,11 +85,13 @@ SIGNATURES = {
     "vgm_dgemm_nt": (C.c_int, [_P(GemmArgs), C.c_void_p]),
     "vgm_dgemm_dot_tiles": (C.c_int, [C.c_int, C.c_int]),
     "vgm_dgemm_set_variant": (C.c_int, [C.c_int]),
-    "vgm_profile_gemm_enable": (C.c_int, [C.c_int]),
-    "vgm_profile_gemm_collect": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
+    "vgm_band_halfwidth": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, C.c_double, _P(C.c_int), C.c_void_p]),
+    "vgm_profile_enable": (C.c_int, [C.c_int]),
+    "vgm_profile_collect": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
     "vgm_convert_bf16": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, C.c_void_p]),
-    "vgm_tc_gemm_bf16": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_dp,
-                                   C.c_int, c_dp, c_dp, C.c_int, C.c_void_p]),
+    "vgm_split_bf16": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, C.c_void_p]),
+    "vgm_tc_gemm_bf16": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp,
+                                   C.c_int, C.c_void_p]),
     "vgm_transpose": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vgm_gm_operators_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vgm_gm_operators": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_size_t,

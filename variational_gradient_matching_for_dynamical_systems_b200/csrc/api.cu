@@ -1,7 +1,10 @@
 // Error reporting + the whole-iteration entry points of libvgm_b200.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "vgm_common.cuh"
+#include "vgm_profile.cuh"
 
 namespace vgm {
 
@@ -16,12 +19,74 @@ void set_error(const char* fmt, ...) {
 
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s);
 
+// ---- per-family CUDA-event profile ------------------------------------------------------
+struct ProfFamily {
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop), reused across collections
+  size_t used = 0;
+  double flops = 0.0, bytes = 0.0;
+  long long launches = 0;
+};
+static bool g_prof_on = false;
+static ProfFamily g_prof[PROF_FAMILIES];
+
+ProfScope::ProfScope(int fam, double flops, double bytes, cudaStream_t s) : family(fam), stream(s), stop(nullptr), active(false) {
+  if (!g_prof_on || fam < 0 || fam >= PROF_FAMILIES) return;
+  ProfFamily& f = g_prof[fam];
+  while (f.used + 2 > f.ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    f.ev.push_back(e);
+  }
+  if (cudaEventRecord(f.ev[f.used], s) != cudaSuccess) return;
+  stop = f.ev[f.used + 1];
+  f.used += 2;
+  f.flops += flops;
+  f.bytes += bytes;
+  f.launches += 1;
+  active = true;
+}
+ProfScope::~ProfScope() {
+  if (active) cudaEventRecord(stop, stream);
+}
+
 }  // namespace vgm
 
 using namespace vgm;
 
 extern "C" const char* vgm_last_error(void) { return g_err; }
-extern "C" int vgm_version(void) { return 100; }
+extern "C" int vgm_version(void) { return 101; }
+
+extern "C" int vgm_profile_enable(int on) {
+  g_prof_on = (on != 0);
+  for (int f = 0; f < PROF_FAMILIES; ++f) {
+    g_prof[f].used = 0;
+    g_prof[f].flops = g_prof[f].bytes = 0.0;
+    g_prof[f].launches = 0;
+  }
+  return VGM_OK;
+}
+
+// Sum of the CUDA-event durations of every launch of `family` since the last enable/collect
+// (synchronises the device), with the algorithmic flops / bytes of those launches and their count.
+extern "C" int vgm_profile_collect(int family, double* flops, double* bytes, double* ms, long long* launches) {
+  VGM_REQUIRE(family >= 0 && family < PROF_FAMILIES, "profile family");
+  VGM_CUDA_OK(cudaDeviceSynchronize());
+  ProfFamily& f = g_prof[family];
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < f.used; i += 2) {
+    float t = 0.f;
+    VGM_CUDA_OK(cudaEventElapsedTime(&t, f.ev[i], f.ev[i + 1]));
+    total += t;
+  }
+  if (flops) *flops = f.flops;
+  if (bytes) *bytes = f.bytes;
+  if (ms) *ms = total;
+  if (launches) *launches = f.launches;
+  f.used = 0;
+  f.flops = f.bytes = 0.0;
+  f.launches = 0;
+  return VGM_OK;
+}
 
 // ---------------------------------------------------------------------------------------
 // One coordinate-ascent iteration = theta update (proxies...py:41-139, analytical) followed by
@@ -56,6 +121,7 @@ extern "C" int vgm_iteration_device(const vgm_program* prog, const vgm_model_tab
   g.lda = g.ldb = g.ldc = plan->ld;
   g.N = model->n_states; g.M = plan->T; g.K = plan->T;
   g.alpha = 1.0;
+  g.band = ops->band_D;
   VGM_TRY(dgemm_nt(g, s));
   VGM_TRY(vgm_param_stats(prog, X, DX, plan->ld, plan->T, model->n_odes, model->ode_class, model->ode_idx,
                           model->ode_state, stats, ws_stats, stats_ws, stream));

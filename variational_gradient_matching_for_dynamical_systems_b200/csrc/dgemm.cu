@@ -13,9 +13,8 @@
 // (a T x T operator, 8 MB at T=1000) stays L2 resident; the A operand streams from HBM once
 // per column-tile sweep.  Operands are staged through a 4-deep cp.async ring in shared
 // memory with a +4 double row pad (conflict-free 64-bit fragment loads).
-#include <vector>
-
 #include "vgm_common.cuh"
+#include "vgm_profile.cuh"
 
 namespace vgm {
 
@@ -70,7 +69,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
     b_dst[i] = r * LDS + 2 * c;
   }
   const int kc_of_thread = 2 * (tid % CPR);         // same column offset for every chunk of this thread
-  const int KT = (a.K + BK - 1) / BK;
+  // Banded operator: B[m][k] is (numerically) zero for |m - k| > band, so this column tile only needs
+  // k in [m0 - band, m0 + BN + band).  band <= 0: dense.
+  int kt_lo = 0, KT = (a.K + BK - 1) / BK;
+  if (a.band > 0) {
+    kt_lo = max(0, m0 - a.band) / BK;
+    KT = min(KT, (min(a.K, m0 + BN + a.band) + BK - 1) / BK);
+  }
 
   auto load_stage = [&](int kt) {
     const int st = kt % STAGES;
@@ -96,11 +101,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_stage(s);
+    if (kt_lo + s < KT) load_stage(kt_lo + s);
     cp_async_commit();
   }
 
-  for (int kt = 0; kt < KT; ++kt) {
+  for (int kt = kt_lo; kt < KT; ++kt) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     {  // prefetch tile kt+STAGES-1 into the slot freed by iteration kt-1
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
   // ---- epilogue ---------------------------------------------------------------------
   // thread owns rows {g, g+8} of each 16-row tile and column pairs (2t, 2t+1) of each 8-col tile
   const bool want_dot = (a.dot_out != nullptr);
+  const bool dot_self = (a.dotw == a.C);
   __shared__ double dot_sm[Cfg::WARPS_N][BM];
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
@@ -175,8 +181,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
             a.C[o] = v0;
           }
           if (want_dot) {
-            dsum += a.dotw[o] * v0;
-            if (two) dsum += a.dotw[o + 1] * v1;
+            if (dot_self) {          // dotw == C: squared row norm of the result
+              dsum += v0 * v0;
+              if (two) dsum += v1 * v1;
+            } else {
+              dsum += a.dotw[o] * v0;
+              if (two) dsum += a.dotw[o + 1] * v1;
+            }
           }
         }
       }
@@ -231,35 +242,23 @@ int gemm_dot_tiles(int M, int N) {
   return ceil_div(M, g_variant == 2 ? CfgV2::BN : CfgBig::BN);
 }
 
-// ---- optional per-launch CUDA-event profile of the GEMM (bench.py roofline) ----------------
-struct GemmProfile {
-  bool enabled = false;
-  std::vector<cudaEvent_t> ev;   // pairs (start, stop), reused across collections
-  size_t used = 0;
-  double flops = 0.0;
-  long long launches = 0;
-};
-static GemmProfile g_prof;
-
 static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s);
 
+// Executed contraction length summed over column tiles of width bn (the band skips the rest).
+static double banded_k_sum(int M, int K, int band, int bn) {
+  if (band <= 0) return (double)ceil_div(M, bn) * K;
+  double sum = 0.0;
+  for (int m0 = 0; m0 < M; m0 += bn) sum += (double)(min(K, m0 + bn + band) - max(0, m0 - band));
+  return sum;
+}
+
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s) {
-  if (!g_prof.enabled || a.N == 0) return dgemm_dispatch(a, s);
-  if (g_prof.used + 2 > g_prof.ev.size()) {
-    for (int i = 0; i < 2; ++i) {
-      cudaEvent_t e;
-      VGM_CUDA_OK(cudaEventCreate(&e));
-      g_prof.ev.push_back(e);
-    }
-  }
-  cudaEvent_t e0 = g_prof.ev[g_prof.used], e1 = g_prof.ev[g_prof.used + 1];
-  VGM_CUDA_OK(cudaEventRecord(e0, s));
-  int rc = dgemm_dispatch(a, s);
-  VGM_CUDA_OK(cudaEventRecord(e1, s));
-  g_prof.used += 2;
-  g_prof.flops += 2.0 * a.N * a.M * a.K;
-  g_prof.launches += 1;
-  return rc;
+  // executed flops (a banded operator skips the k range that is numerically zero) and compulsory bytes
+  const int bn = 64;
+  const double flops = 2.0 * a.N * bn * banded_k_sum(a.M, a.K, a.band, bn);
+  const double bytes = 8.0 * ((double)a.N * a.K + (double)a.N * a.M);
+  ProfScope prof(PROF_DGEMM, flops, bytes, s);
+  return dgemm_dispatch(a, s);
 }
 
 static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s) {
@@ -292,33 +291,6 @@ extern "C" int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream) {
 // Tuning knob (tile configuration of the large-N GEMM); 2 is the default.
 extern "C" int vgm_dgemm_set_variant(int v) {
   vgm::g_variant = v;
-  return VGM_OK;
-}
-
-extern "C" int vgm_profile_gemm_enable(int on) {
-  vgm::g_prof.enabled = (on != 0);
-  vgm::g_prof.used = 0;
-  vgm::g_prof.flops = 0.0;
-  vgm::g_prof.launches = 0;
-  return VGM_OK;
-}
-
-// Sum of the CUDA-event durations of every DGEMM launched since the last enable/collect
-// (synchronises the device), the algorithmic flops 2*N*M*K of those launches and their count.
-extern "C" int vgm_profile_gemm_collect(double* flops, double* ms, long long* launches) {
-  VGM_CUDA_OK(cudaDeviceSynchronize());
-  double total = 0.0;
-  for (size_t i = 0; i + 1 < vgm::g_prof.used; i += 2) {
-    float t = 0.f;
-    VGM_CUDA_OK(cudaEventElapsedTime(&t, vgm::g_prof.ev[i], vgm::g_prof.ev[i + 1]));
-    total += t;
-  }
-  if (flops) *flops = vgm::g_prof.flops;
-  if (ms) *ms = total;
-  if (launches) *launches = vgm::g_prof.launches;
-  vgm::g_prof.used = 0;
-  vgm::g_prof.flops = 0.0;
-  vgm::g_prof.launches = 0;
   return VGM_OK;
 }
 

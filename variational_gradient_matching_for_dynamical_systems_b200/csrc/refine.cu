@@ -1,0 +1,267 @@
+// Vector kernels of the mixed-precision solver (one CTA per system row; every kernel streams each array
+// once, 16-byte vector accesses, row-wide reductions through shared memory) and the band-width probe.
+//
+// The correction solves A_u d = r_u, A_u = M + diag(Lambda_u) (proxies_for_ode_parameters_and_states.py:232,
+// 245,262 solve the same system with LAPACK), run as FP32 preconditioned CG whose two operator products
+// per step are tcgen05 GEMMs (tc_gemm.cu) writing raw FP32 accumulators; everything elementwise and every
+// dot product of a CG step lives in the two kernels ir_update / ir_dir below.
+#include <cuda_bf16.h>
+
+#include "vgm_common.cuh"
+#include "vgm_profile.cuh"
+#include "refine.cuh"
+
+namespace vgm {
+
+constexpr int IR_THREADS = 256;
+
+size_t ir_ws_bytes(int n, int ld) {
+  const size_t f32 = align_up((size_t)n * ld * sizeof(float), 256);
+  const size_t b16 = align_up((size_t)n * ld * sizeof(__nv_bfloat16), 256);
+  const size_t vec = align_up((size_t)n * sizeof(double), 256);
+  return 4 * f32 + 4 * b16 + 2 * vec;
+}
+
+void ir_carve(char*& p, int n, int ld, IrBuf& b) {
+  const size_t f32 = align_up((size_t)n * ld * sizeof(float), 256);
+  const size_t b16 = align_up((size_t)n * ld * sizeof(__nv_bfloat16), 256);
+  const size_t vec = align_up((size_t)n * sizeof(double), 256);
+  b.r32 = (float*)p; p += f32;
+  b.d32 = (float*)p; p += f32;
+  b.acc32 = (float*)p; p += f32;
+  b.lam32 = (float*)p; p += f32;
+  b.p_hi = (__nv_bfloat16*)p; p += b16;
+  b.p_lo = (__nv_bfloat16*)p; p += b16;
+  b.rsb = (__nv_bfloat16*)p; p += b16;
+  b.s16 = (__nv_bfloat16*)p; p += b16;
+  b.sigma = (double*)p; p += vec;
+  b.rz = (double*)p; p += vec;
+}
+
+// ---- 4-element vector helpers (rows are 16-byte aligned: ld % 8 == 0) --------------------------------
+struct bf4 { __nv_bfloat162 a, b; };
+__device__ __forceinline__ float4 ld_bf4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void st_bf4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo);
+  u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float bf_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// The GEMM writes columns < T only: whatever sits in the row padding of acc32 must not reach a dot product.
+__device__ __forceinline__ float4 ld_acc4(const float* p, int i, int T) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  if (i + 4 > T) {
+    if (i + 1 >= T) v.y = 0.f;
+    if (i + 2 >= T) v.z = 0.f;
+    if (i + 3 >= T) v.w = 0.f;
+  }
+  return v;
+}
+
+// Loop over the 4-element groups of one row; the last group may be partial (T % 4 != 0 is handled by the
+// zero padding of every row up to ld, which all kernels preserve).
+#define IR_ROW_LOOP(i, T) for (int i = 4 * threadIdx.x; i < (T); i += 4 * IR_THREADS)
+
+__global__ void __launch_bounds__(IR_THREADS)
+ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __restrict__ Lambda,
+                     const double* __restrict__ rr, const int* __restrict__ act, int T, int ld, double shift,
+                     double c) {
+  const int j = blockIdx.x;
+  const int slot = act[j];
+  const double sig = sqrt(rr[slot]);
+  const double inv = sig > 0.0 ? 1.0 / sig : 0.0;
+  const size_t oj = (size_t)j * ld, os = (size_t)slot * ld;
+  IR_ROW_LOOP(i, T) {
+    float4 r, lam, sv;
+    float* rp = &r.x; float* lp = &lam.x; float* sp = &sv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = i + e < T;
+      const double L = ok ? Lambda[os + i + e] : 0.0;
+      rp[e] = ok ? (float)(R[os + i + e] * inv) : 0.f;
+      lp[e] = (float)L;
+      sp[e] = ok ? ((c > 0.0) ? bf_round((float)sqrt((shift + c) / (L + c))) : 1.f) : 0.f;
+    }
+    *reinterpret_cast<float4*>(b.r32 + oj + i) = r;
+    *reinterpret_cast<float4*>(b.lam32 + oj + i) = lam;
+    *reinterpret_cast<float4*>(b.d32 + oj + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    st_bf4(b.s16 + oj + i, sv);
+    st_bf4(b.rsb + oj + i, make_float4(sv.x * r.x, sv.y * r.y, sv.z * r.z, sv.w * r.w));
+  }
+  if (threadIdx.x == 0) b.sigma[j] = sig;
+}
+
+__global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, int T, int ld, int first) {
+  extern __shared__ float ir_sm[];       // z of this row
+  __shared__ double red[40];
+  const int j = blockIdx.x;
+  const size_t o = (size_t)j * ld;
+  double part = 0.0;
+  IR_ROW_LOOP(i, T) {
+    const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
+    const float4 sv = ld_bf4(b.s16 + o + i);
+    const float4 r = *reinterpret_cast<const float4*>(b.r32 + o + i);
+    const float4 z = make_float4(sv.x * acc.x, sv.y * acc.y, sv.z * acc.z, sv.w * acc.w);
+    *reinterpret_cast<float4*>(ir_sm + i) = z;
+    part += (double)r.x * z.x + (double)r.y * z.y + (double)r.z * z.z + (double)r.w * z.w;
+  }
+  const double rz_new = block_sum(part, red);
+  const double rz_old = first ? 0.0 : b.rz[j];
+  const float beta = (first || !(rz_old > 0.0)) ? 0.f : (float)(rz_new / rz_old);
+  IR_ROW_LOOP(i, T) {
+    float4 p = *reinterpret_cast<const float4*>(ir_sm + i);
+    if (!first) {
+      const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
+      p.x += beta * (h.x + l.x); p.y += beta * (h.y + l.y); p.z += beta * (h.z + l.z); p.w += beta * (h.w + l.w);
+    }
+    const float4 hi = make_float4(bf_round(p.x), bf_round(p.y), bf_round(p.z), bf_round(p.w));
+    st_bf4(b.p_hi + o + i, hi);
+    st_bf4(b.p_lo + o + i, make_float4(p.x - hi.x, p.y - hi.y, p.z - hi.z, p.w - hi.w));
+  }
+  if (threadIdx.x == 0) b.rz[j] = rz_new;
+}
+
+__global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, int T, int ld, int last) {
+  extern __shared__ float ir_sm[];       // p and q of this row
+  __shared__ double red[40];
+  float* sp = ir_sm;
+  float* sq = ir_sm + ((T + 3) & ~3);
+  const int j = blockIdx.x;
+  const size_t o = (size_t)j * ld;
+  double part = 0.0;
+  IR_ROW_LOOP(i, T) {
+    const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
+    const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
+    const float4 lam = *reinterpret_cast<const float4*>(b.lam32 + o + i);
+    const float4 p = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+    const float4 q = make_float4(fmaf(lam.x, p.x, acc.x), fmaf(lam.y, p.y, acc.y), fmaf(lam.z, p.z, acc.z),
+                                 fmaf(lam.w, p.w, acc.w));
+    *reinterpret_cast<float4*>(sp + i) = p;
+    *reinterpret_cast<float4*>(sq + i) = q;
+    part += (double)p.x * q.x + (double)p.y * q.y + (double)p.z * q.z + (double)p.w * q.w;
+  }
+  const double pq = block_sum(part, red);
+  const float alpha = (pq > 0.0) ? (float)(b.rz[j] / pq) : 0.f;
+  IR_ROW_LOOP(i, T) {
+    const float4 p = *reinterpret_cast<const float4*>(sp + i);
+    const float4 q = *reinterpret_cast<const float4*>(sq + i);
+    float4 d = *reinterpret_cast<const float4*>(b.d32 + o + i);
+    d.x = fmaf(alpha, p.x, d.x); d.y = fmaf(alpha, p.y, d.y); d.z = fmaf(alpha, p.z, d.z); d.w = fmaf(alpha, p.w, d.w);
+    *reinterpret_cast<float4*>(b.d32 + o + i) = d;
+    if (!last) {
+      float4 r = *reinterpret_cast<const float4*>(b.r32 + o + i);
+      r.x = fmaf(-alpha, q.x, r.x); r.y = fmaf(-alpha, q.y, r.y); r.z = fmaf(-alpha, q.z, r.z); r.w = fmaf(-alpha, q.w, r.w);
+      *reinterpret_cast<float4*>(b.r32 + o + i) = r;
+      const float4 sv = ld_bf4(b.s16 + o + i);
+      st_bf4(b.rsb + o + i, make_float4(sv.x * r.x, sv.y * r.y, sv.z * r.z, sv.w * r.w));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(IR_THREADS)
+ir_finish_kernel(IrBuf b, double* __restrict__ P, double* __restrict__ X, const int* __restrict__ slot_state,
+                 const int* __restrict__ act, int T, int ld) {
+  const int j = blockIdx.x;
+  const int slot = act[j];
+  const double sig = b.sigma[j];
+  const float* d = b.d32 + (size_t)j * ld;
+  double* p = P + (size_t)slot * ld;
+  double* x = X + (size_t)slot_state[slot] * ld;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const double v = p[t] + sig * (double)d[t];
+    p[t] = v;
+    x[t] = v;
+  }
+}
+
+int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
+                  int T, int ld, double shift, double c, cudaStream_t s) {
+  if (n <= 0) return VGM_OK;
+  ProfScope prof(PROF_VEC, 0.0, (double)n * T * (16.0 + 16.0), s);
+  ir_inner_init_kernel<<<n, IR_THREADS, 0, s>>>(b, R, Lambda, rr, act, T, ld, shift, c);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+int ir_dir(const IrBuf& b, int n, int T, int ld, int first, cudaStream_t s) {
+  if (n <= 0) return VGM_OK;
+  // reads acc32 4, s16 2, r32 4, (p_hi, p_lo 4); writes p_hi, p_lo 4
+  ProfScope prof(PROF_VEC, 0.0, (double)n * T * (first ? 14.0 : 18.0), s);
+  ir_dir_kernel<<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, first);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+int ir_update(const IrBuf& b, int n, int T, int ld, int last, cudaStream_t s) {
+  if (n <= 0) return VGM_OK;
+  // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4, s16 2); writes d32 4, (r32 4, rsb 2)
+  ProfScope prof(PROF_VEC, 0.0, (double)n * T * (last ? 20.0 : 32.0), s);
+  ir_update_kernel<<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, last);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, int T, int ld,
+              cudaStream_t s) {
+  if (n <= 0) return VGM_OK;
+  ProfScope prof(PROF_VEC, 0.0, (double)n * T * 28.0, s);
+  ir_finish_kernel<<<n, IR_THREADS, 0, s>>>(b, P, X, slot_state, act, T, ld);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+// ---- band-width probe ---------------------------------------------------------------------------------
+__global__ void band_absmax_kernel(const double* __restrict__ B, int rows, int cols, int ld, double* __restrict__ out) {
+  __shared__ double red[40];
+  double m = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * cols; i += (size_t)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(B[(i / cols) * ld + (i % cols)]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+  }
+}
+__global__ void band_width_kernel(const double* __restrict__ B, int rows, int cols, int ld, double rel,
+                                  const double* __restrict__ absmax, int* __restrict__ band) {
+  const double thr = rel * absmax[0];
+  int w = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)rows * cols; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const double v = fabs(B[(size_t)r * ld + c]);
+    if (v > thr || v != v) w = max(w, abs(r - c));
+  }
+  for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+  if ((threadIdx.x & 31) == 0 && w > 0) atomicMax(band, w);
+}
+
+}  // namespace vgm
+
+extern "C" int vgm_band_halfwidth(const double* B, int rows, int cols, int ld, double rel_threshold, int* band_host,
+                                  vgm_stream_t stream) {
+  VGM_REQUIRE(B && band_host && rows > 0 && cols > 0 && ld >= cols && rel_threshold >= 0.0, "band arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  void* scratch = nullptr;
+  VGM_CUDA_OK(cudaMallocAsync(&scratch, 16, s));
+  VGM_CUDA_OK(cudaMemsetAsync(scratch, 0, 16, s));
+  double* absmax = (double*)scratch;
+  int* band = (int*)((char*)scratch + 8);
+  const int blocks = 296;
+  vgm::band_absmax_kernel<<<blocks, 256, 0, s>>>(B, rows, cols, ld, absmax);
+  vgm::band_width_kernel<<<blocks, 256, 0, s>>>(B, rows, cols, ld, rel_threshold, absmax, band);
+  VGM_LAUNCH_OK();
+  VGM_CUDA_OK(cudaMemcpyAsync(band_host, band, sizeof(int), cudaMemcpyDeviceToHost, s));
+  VGM_CUDA_OK(cudaFreeAsync(scratch, s));
+  VGM_CUDA_OK(cudaStreamSynchronize(s));
+  return VGM_OK;
+}

@@ -1,0 +1,30 @@
+// Low-precision side of the mixed-precision (iterative refinement) solver: buffers and vector kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace vgm {
+
+// All arrays are COMPACT: row j belongs to the j-th entry of the current active list.
+struct IrBuf {
+  float *r32, *d32, *acc32, *lam32;       // [n][ld] residual, correction, GEMM output (q' or z'), Lambda
+  __nv_bfloat16 *p_hi, *p_lo;             // [n][ld] search direction p = hi + lo (the tensor-core A operand)
+  __nv_bfloat16 *rsb, *s16;               // [n][ld] bf16(s o r) (A operand of the preconditioner GEMM), scaling s
+  double *sigma, *rz;                     // [n] residual norm each row was scaled by; r.z
+};
+
+size_t ir_ws_bytes(int n, int ld);
+void ir_carve(char*& p, int n, int ld, IrBuf& b);
+
+// r32 = R[slot]/sigma, lam32 = Lambda[slot], s = sqrt((shift + c)/(Lambda + c)) (1 if c <= 0), rsb = bf16(s r), d = 0
+int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
+                  int T, int ld, double shift, double c, cudaStream_t s);
+// z = s o acc32; rz' = r.z; beta = first ? 0 : rz'/rz; p = z + beta p  ->  (p_hi, p_lo)
+int ir_dir(const IrBuf& b, int n, int T, int ld, int first, cudaStream_t s);
+// q = acc32 + lam o p; alpha = rz / p.q; d += alpha p; r -= alpha q; rsb = bf16(s o r)
+int ir_update(const IrBuf& b, int n, int T, int ld, int last, cudaStream_t s);
+// x = P[slot] + sigma d; P[slot] = x; X[state(slot)] = x
+int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, int T, int ld,
+              cudaStream_t s);
+
+}  // namespace vgm

@@ -15,6 +15,9 @@
 #include <cuda_bf16.h>
 
 #include "vgm_common.cuh"
+#include "vgm_profile.cuh"
+#include "tc_gemm.cuh"
+#include "refine.cuh"
 
 struct vgm_program;
 
@@ -23,20 +26,7 @@ namespace vgm {
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s);
 int gemm_dot_tiles(int M, int N);
 
-struct LpGemmArgs {
-  const __nv_bfloat16* A;
-  const __nv_bfloat16* B;
-  double* C;
-  int lda, ldb, ldc;
-  int N, M, K;
-  const int* rows;
-  const int* n_rows_dev;
-  const double* dotw;
-  double* dot_out;
-  int dot_ld;
-};
-int lp_gemm(const LpGemmArgs& a, cudaStream_t s);
-int lp_gemm_dot_tiles(int M);
+
 int program_state_assemble(const vgm_program* prog, const vgm_sweep_plan* pl, const double* X, const double* DX0,
                            const double* theta, double* Lambda, double* rhs, double* ruu, double* Ruu, double* Rlive,
                            cudaStream_t s);
@@ -59,7 +49,6 @@ struct CgBuf {
   int *n_act;                     // device count (2 ints: [0] current, [1] scratch)
   int n_tiles;                    // partial dots per row written by the operator GEMM
   int n_tiles_z;                  // ... by the preconditioner GEMM
-  __nv_bfloat16* Rb;              // [n_hidden][ld] bf16 copy of R (only with the BF16 preconditioner)
 };
 
 __global__ void cg_gather_x_kernel(const double* __restrict__ X, const int* __restrict__ slot_state,
@@ -93,7 +82,6 @@ __global__ void cg_init_kernel(CgBuf cb, const double* __restrict__ rhs, const d
     const double b = rhs[o + t];
     const double r = b - cb.Q[o + t];
     cb.R[o + t] = r;
-    if (cb.Rb) cb.Rb[o + t] = __double2bfloat16(r);
     if (!precond) cb.P[o + t] = r;
     rr += r * r;
     bb += b * b;
@@ -147,7 +135,6 @@ __global__ void cg_update_kernel(CgBuf cb, double* __restrict__ X, const int* __
     x[t] += alpha * p;
     const double r = cb.R[o + t] - alpha * cb.Q[o + t];
     cb.R[o + t] = r;
-    if (cb.Rb) cb.Rb[o + t] = __double2bfloat16(r);
     rr += r * r;
   }
   rr = block_sum(rr, red);
@@ -254,7 +241,8 @@ __global__ void add_live_terms_kernel(const int* __restrict__ live_pair_slot, co
 // ------------------------------------------------------------------------------------
 struct PcgWs {
   CgBuf cb;
-  int* host_poll_dev;  // 2 ints
+  IrBuf ir;                      // low-precision side of the mixed-precision solver
+  int* host_poll_dev;            // 2 ints
 };
 
 static size_t pcg_ws_bytes(int n_hidden, int T, int ld) {
@@ -262,8 +250,7 @@ static size_t pcg_ws_bytes(int n_hidden, int T, int ld) {
   const int n_tiles = ceil_div(T, 64);  // upper bound over GEMM configurations
   const size_t part = align_up((size_t)n_hidden * n_tiles * sizeof(double), 256);
   const size_t vec = align_up((size_t)n_hidden * sizeof(double), 256);
-  const size_t half = align_up((size_t)n_hidden * ld * sizeof(__nv_bfloat16), 256);
-  return 5 * mat + half + 2 * part + 3 * vec + 4 * vec /*done, iters, act x2 (ints fit)*/ + 1024;
+  return 5 * mat + ir_ws_bytes(n_hidden, ld) + 2 * part + 3 * vec + 4 * vec /*done, iters, act x2 (ints fit)*/ + 1024;
 }
 
 static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, PcgWs& w) {
@@ -280,7 +267,7 @@ static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, Pcg
   c.Q = (double*)p; p += mat;
   c.Z = (double*)p; p += mat;
   c.W = (double*)p; p += mat;
-  c.Rb = (__nv_bfloat16*)p; p += align_up((size_t)n_hidden * ld * sizeof(__nv_bfloat16), 256);
+  ir_carve(p, n_hidden, ld, w.ir);
   c.pq_part = (double*)p; p += part;
   c.rz_part = (double*)p; p += part;
   c.rz = (double*)p; p += vec;
@@ -312,6 +299,7 @@ static int apply_operator(const vgm_operators* ops, int ruu_const, const double*
   if (ruu_const) {
     g.A = cb.P; g.B = ops->M; g.C = cb.Q;
     g.alpha = 1.0;
+    g.band = ops->band_M;
     g.U1 = Lambda; g.V1 = cb.P; g.g1 = 1.0;
     if (want_dot) { g.dotw = cb.P; g.dot_out = cb.pq_part; g.dot_ld = cb.n_tiles; }
     VGM_TRY(dgemm_nt(g, s));
@@ -320,6 +308,7 @@ static int apply_operator(const vgm_operators* ops, int ruu_const, const double*
     // W = Ruu o P - D P
     g.A = cb.P; g.B = ops->D; g.C = cb.W;
     g.alpha = -1.0;
+    g.band = ops->band_D;
     g.U1 = Ruu; g.V1 = cb.P; g.g1 = 1.0;
     VGM_TRY(dgemm_nt(g, s));
     // Q = Ruu o W - D^T W + Lambda o P
@@ -333,52 +322,194 @@ static int apply_operator(const vgm_operators* ops, int ruu_const, const double*
   return VGM_OK;
 }
 
-// Z = R G^T with partial dots r.z -> rz_part (FP64 DMMA, or BF16 tensor cores when G_bf16 is given)
+// FP64 preconditioner: Z = R G^T on the DMMA pipe, partial dots r.z -> rz_part.
 static int apply_preconditioner(const vgm_operators* ops, CgBuf& cb, const int* act, int n_upper, int T, int ld,
                                 Counters& cnt, cudaStream_t s) {
-  if (ops->G_bf16) {
-    LpGemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.A = cb.Rb; g.B = (const __nv_bfloat16*)ops->G_bf16; g.C = cb.Z;
-    g.lda = g.ldb = g.ldc = ld;
-    g.N = n_upper; g.M = T; g.K = T;
-    g.rows = act; g.n_rows_dev = cb.n_act;
-    g.dotw = cb.R; g.dot_out = cb.rz_part; g.dot_ld = cb.n_tiles_z;
-    VGM_TRY(lp_gemm(g, s));
-  } else {
-    vgm_gemm_args g;
-    memset(&g, 0, sizeof(g));
-    g.A = cb.R; g.B = ops->G; g.C = cb.Z;
-    g.lda = g.ldb = g.ldc = ld;
-    g.N = n_upper; g.M = T; g.K = T;
-    g.rowsA = act; g.rowsC = act; g.n_rows_dev = cb.n_act;
-    g.alpha = 1.0;
-    g.dotw = cb.R; g.dot_out = cb.rz_part; g.dot_ld = cb.n_tiles_z;
-    VGM_TRY(dgemm_nt(g, s));
-  }
+  vgm_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = cb.R; g.B = ops->G; g.C = cb.Z;
+  g.lda = g.ldb = g.ldc = ld;
+  g.N = n_upper; g.M = T; g.K = T;
+  g.rowsA = act; g.rowsC = act; g.n_rows_dev = cb.n_act;
+  g.alpha = 1.0;
+  g.dotw = cb.R; g.dot_out = cb.rz_part; g.dot_ld = cb.n_tiles_z;
+  VGM_TRY(dgemm_nt(g, s));
   cnt.gemm += 1; cnt.launches += 1;
   return VGM_OK;
 }
 
+// Drop converged rows from the active list and fetch the new count (one 4-byte D2H poll).
+static int compact_and_poll(CgBuf& cb, int& cur, const int*& act, int& n_upper, Counters& cnt, cudaStream_t s) {
+  cg_compact_kernel<<<1, 1024, 0, s>>>(cb.act[cur], cb.act[cur ^ 1], cb.n_act, cb.done);
+  cg_commit_count_kernel<<<1, 1, 0, s>>>(cb.n_act);
+  VGM_LAUNCH_OK();
+  cnt.launches += 2;
+  cur ^= 1;
+  act = cb.act[cur];
+  int host_cnt = 0;
+  VGM_CUDA_OK(cudaMemcpyAsync(&host_cnt, cb.n_act, sizeof(int), cudaMemcpyDeviceToHost, s));
+  VGM_CUDA_OK(cudaStreamSynchronize(s));
+  n_upper = host_cnt;
+  return VGM_OK;
+}
+
+static int report_convergence(CgBuf& cb, PcgWs& w, const int* rows, int n_rows, double tol, int cap,
+                              vgm_sweep_info* info, Counters& cnt, cudaStream_t s) {
+  cg_count_unconverged_kernel<<<1, 256, 0, s>>>(rows, n_rows, cb.done, cb.iters, w.host_poll_dev);
+  VGM_LAUNCH_OK();
+  int res[2] = {0, 0};
+  VGM_CUDA_OK(cudaMemcpyAsync(res, w.host_poll_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  VGM_CUDA_OK(cudaStreamSynchronize(s));
+  cnt.launches += 1;
+  if (info) {
+    info->iterations = max(info->iterations, res[1]);
+    info->unconverged += res[0];
+  }
+  if (res[0] > 0) {
+    set_error("solver: %d of %d systems did not reach tol=%g within %d iterations", res[0], n_rows, tol, cap);
+    return VGM_ENOTCONV;
+  }
+  return VGM_OK;
+}
+
+// ---- mixed-precision iterative refinement ----------------------------------------------------------------
+// bb = ||rhs||^2; rows without a self pair are solved directly, x = rhs / (2 Lambda) (alias quirk,
+// proxies...py:201,245); a zero right-hand side gives x = 0.
+__global__ void ir_prep_kernel(CgBuf cb, const double* __restrict__ rhs, const double* __restrict__ Lambda,
+                               double* __restrict__ X, const int* __restrict__ slot_state,
+                               const int* __restrict__ slot_has_self, const int* __restrict__ act, int T, int ld) {
+  __shared__ double red[40];
+  const int slot = act[blockIdx.x];
+  const size_t o = (size_t)slot * ld;
+  double* x = X + (size_t)slot_state[slot] * ld;
+  if (slot_has_self && !slot_has_self[slot]) {
+    for (int t = threadIdx.x; t < T; t += blockDim.x) x[t] = rhs[o + t] / (2.0 * Lambda[o + t]);
+    if (threadIdx.x == 0) { cb.done[slot] = 1; cb.iters[slot] = 0; }
+    return;
+  }
+  double bb = 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) bb += rhs[o + t] * rhs[o + t];
+  bb = block_sum(bb, red);
+  if (bb == 0.0)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) x[t] = 0.0;
+  if (threadIdx.x == 0) {
+    cb.bb[slot] = bb;
+    cb.iters[slot] = 0;
+    cb.done[slot] = (bb == 0.0) ? 1 : 0;
+  }
+}
+
+// rr = ||r||^2 from the residual GEMM's partial dots; convergence test of the outer iteration.
+__global__ void ir_check_kernel(CgBuf cb, const int* __restrict__ act, int n_tiles, double tol2, int outer, int inner) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *cb.n_act) return;
+  const int slot = act[j];
+  if (cb.done[slot]) return;
+  double rr = 0.0;
+  for (int i = 0; i < n_tiles; ++i) rr += cb.pq_part[(size_t)slot * n_tiles + i];
+  cb.rr[slot] = rr;
+  cb.iters[slot] = outer * inner;
+  if (rr <= tol2 * cb.bb[slot]) cb.done[slot] = 1;
+}
+
+// Solve (M + diag Lambda_u) x_u = rhs_u for the rows of one dependency level:
+//   outer (FP64, DMMA):  r = rhs - (x M^T + Lambda o x), test ||r|| <= tol ||rhs||, x += sigma d
+//   inner (FP32 vectors): `inner` steps of PCG on A d = r / sigma with the operator applied as a bf16-split
+//                         tcgen05 GEMM (3 products, ~2^-16) and the preconditioner S G S (G = (M + shift I)^-1
+//                         in bf16, S the diagonal scaling of vgm_operators.precond_c).
+// Each correction contracts the error by ~1e-3..1e-4, so 4-5 FP64 GEMMs replace the ~60 of FP64 PCG.
+static int ir_solve(const vgm_operators* ops, const double* Lambda, const double* rhs, double* X,
+                    const int* slot_state, const int* slot_has_self, const int* rows, int n_rows, int T, int ld,
+                    const vgm_solver_opts* opts, PcgWs& w, vgm_sweep_info* info, Counters& cnt, cudaStream_t s) {
+  const double tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
+  const int max_outer = (opts && opts->max_iter > 0) ? opts->max_iter : 30;
+  const int inner = (opts && opts->inner_iters > 0) ? opts->inner_iters : 10;
+  CgBuf& cb = w.cb;
+  IrBuf& ir = w.ir;
+  const int th = row_threads(T);
+  const __nv_bfloat16* M_hi = (const __nv_bfloat16*)ops->M_bf16x2;
+  const __nv_bfloat16* M_lo = M_hi + (size_t)T * ld;
+
+  VGM_CUDA_OK(cudaMemcpyAsync(cb.act[0], rows, (size_t)n_rows * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  cg_set_count_kernel<<<1, 1, 0, s>>>(cb.n_act, n_rows);
+  int cur = 0;
+  const int* act = cb.act[0];
+  {
+    ProfScope prof(PROF_VEC, 0.0, (double)n_rows * T * 24.0, s);
+    ir_prep_kernel<<<n_rows, th, 0, s>>>(cb, rhs, Lambda, X, slot_state, slot_has_self, act, T, ld);
+    cg_gather_x_kernel<<<n_rows, th, 0, s>>>(X, slot_state, act, cb.n_act, T, ld, cb.P);
+  }
+  VGM_LAUNCH_OK();
+  cnt.launches += 4;
+
+  int n_upper = n_rows;
+  for (int outer = 0; outer <= max_outer && n_upper > 0; ++outer) {
+    // R = rhs - P M^T - Lambda o P, squared row norms -> pq_part
+    cb.n_tiles = gemm_dot_tiles(T, n_upper);
+    vgm_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.A = cb.P; g.B = ops->M; g.C = cb.R;
+    g.lda = g.ldb = g.ldc = ld;
+    g.N = n_upper; g.M = T; g.K = T;
+    g.rowsA = act; g.rowsC = act; g.n_rows_dev = cb.n_act;
+    g.alpha = -1.0; g.beta = 1.0; g.C0 = rhs;
+    g.U1 = Lambda; g.V1 = cb.P; g.g1 = -1.0;
+    g.dotw = cb.R; g.dot_out = cb.pq_part; g.dot_ld = cb.n_tiles;
+    g.band = ops->band_M;
+    VGM_TRY(dgemm_nt(g, s));
+    ir_check_kernel<<<ceil_div(n_upper, 256), 256, 0, s>>>(cb, act, cb.n_tiles, tol * tol, outer, inner);
+    VGM_LAUNCH_OK();
+    cnt.gemm += 1; cnt.launches += 2;
+    VGM_TRY(compact_and_poll(cb, cur, act, n_upper, cnt, s));
+    if (n_upper == 0 || outer == max_outer) break;
+
+    const int n = n_upper;
+    VGM_TRY(ir_inner_init(ir, cb.R, Lambda, cb.rr, act, n, T, ld, ops->G_shift, ops->precond_c, s));
+    TcGemmArgs tg;
+    memset(&tg, 0, sizeof(tg));
+    tg.n_rows = n; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = ir.acc32; tg.ldo = ld;
+    TcGemmArgs tp = tg;                                   // z' = (s o r) G^T
+    tp.A0 = ir.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
+    TcGemmArgs to = tg;                                   // q' = p M^T (bf16 split)
+    to.A0 = ir.p_hi; to.A1 = ir.p_lo; to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M;
+    VGM_TRY(tc_gemm(tp, s));
+    VGM_TRY(ir_dir(ir, n, T, ld, 1, s));
+    cnt.launches += 3; cnt.gemm += 1;
+    for (int it = 0; it < inner; ++it) {
+      const int last = (it == inner - 1) ? 1 : 0;
+      VGM_TRY(tc_gemm(to, s));
+      VGM_TRY(ir_update(ir, n, T, ld, last, s));
+      cnt.launches += 2; cnt.gemm += 1;
+      if (last) break;
+      VGM_TRY(tc_gemm(tp, s));
+      VGM_TRY(ir_dir(ir, n, T, ld, 0, s));
+      cnt.launches += 2; cnt.gemm += 1;
+    }
+    VGM_TRY(ir_finish(ir, cb.P, X, slot_state, act, n, T, ld, s));
+    cnt.launches += 1;
+  }
+  return report_convergence(cb, w, rows, n_rows, tol, max_outer * inner, info, cnt, s);
+}
+
 static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu, const double* Lambda,
                      const double* rhs, double* X, const int* slot_state, const int* slot_has_self, const int* rows,
-                     int n_rows, int T, int ld, const vgm_solver_opts* opts, PcgWs& w, vgm_sweep_info* info,
-                     Counters& cnt, cudaStream_t s) {
+                     int n_rows, int n_hidden, int T, int ld, const vgm_solver_opts* opts, PcgWs& w,
+                     vgm_sweep_info* info, Counters& cnt, cudaStream_t s) {
   if (n_rows == 0) return VGM_OK;
   VGM_REQUIRE(ops && ops->D && ops->DT, "operators D and DT are required");
   VGM_REQUIRE(!ruu_const || ops->M, "shared operator M is required when R_uu is constant");
   VGM_REQUIRE(ruu_const || Ruu, "R_uu array is required when it is not constant");
+  // mixed precision needs the bf16 operators and tiles that the TMA boxes (128 x 64) fit into
+  if (ruu_const && ops->G_bf16 && ops->M_bf16x2 && T >= 128)
+    return ir_solve(ops, Lambda, rhs, X, slot_state, slot_has_self, rows, n_rows, T, ld, opts, w, info, cnt, s);
   const double tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
   const int max_iter = (opts && opts->max_iter > 0) ? opts->max_iter : 4 * T;
   const int check_every = (opts && opts->check_every > 0) ? opts->check_every : 8;
-  const int precond = (ruu_const && (ops->G || ops->G_bf16)) ? 1 : 0;
+  const int precond = (ruu_const && ops->G) ? 1 : 0;
   const double tol2 = tol * tol;
   CgBuf& cb = w.cb;
   cb.n_tiles = gemm_dot_tiles(T, n_rows);
-  const bool lp = precond && ops->G_bf16 != nullptr;
-  cb.n_tiles_z = lp ? lp_gemm_dot_tiles(T) : cb.n_tiles;
-  __nv_bfloat16* const rb_keep = cb.Rb;
-  if (!lp) cb.Rb = nullptr;      // the vector kernels only maintain the bf16 residual when it is used
+  cb.n_tiles_z = cb.n_tiles;
   const int th = row_threads(T);
 
   VGM_CUDA_OK(cudaMemcpyAsync(cb.act[0], rows, (size_t)n_rows * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -400,7 +531,6 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
 
   int n_upper = n_rows;  // host-side upper bound of the active count
   int it = 0;
-  int host_cnt[2] = {n_rows, 0};
   while (it < max_iter && n_upper > 0) {
     const int burst = min(check_every, max_iter - it);
     for (int b = 0; b < burst; ++b, ++it) {
@@ -416,35 +546,12 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
       }
     }
     // drop converged rows, then poll the new count
-    cg_compact_kernel<<<1, 1024, 0, s>>>(cb.act[cur], cb.act[cur ^ 1], cb.n_act, cb.done);
-    cg_commit_count_kernel<<<1, 1, 0, s>>>(cb.n_act);
-    VGM_LAUNCH_OK();
-    cnt.launches += 2;
-    cur ^= 1;
-    act = cb.act[cur];
-    VGM_CUDA_OK(cudaMemcpyAsync(host_cnt, cb.n_act, sizeof(int), cudaMemcpyDeviceToHost, s));
-    VGM_CUDA_OK(cudaStreamSynchronize(s));
-    n_upper = host_cnt[0];
+    VGM_TRY(compact_and_poll(cb, cur, act, n_upper, cnt, s));
     // the GEMM tile configuration (hence the number of partial dots per row) follows the host bound
     cb.n_tiles = gemm_dot_tiles(T, n_upper > 0 ? n_upper : 1);
-    if (!lp) cb.n_tiles_z = cb.n_tiles;
+    cb.n_tiles_z = cb.n_tiles;
   }
-  cb.Rb = rb_keep;
-  cg_count_unconverged_kernel<<<1, 256, 0, s>>>(rows, n_rows, cb.done, cb.iters, w.host_poll_dev);
-  VGM_LAUNCH_OK();
-  int res[2] = {0, 0};
-  VGM_CUDA_OK(cudaMemcpyAsync(res, w.host_poll_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  VGM_CUDA_OK(cudaStreamSynchronize(s));
-  cnt.launches += 1;
-  if (info) {
-    info->iterations = max(info->iterations, res[1]);
-    info->unconverged += res[0];
-  }
-  if (res[0] > 0) {
-    set_error("PCG: %d of %d systems did not reach tol=%g within %d iterations", res[0], n_rows, tol, max_iter);
-    return VGM_ENOTCONV;
-  }
-  return VGM_OK;
+  return report_convergence(cb, w, rows, n_rows, tol, max_iter, info, cnt, s);
 }
 
 // ------------------------------------------------------------------------------------
@@ -505,6 +612,7 @@ static int state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* pl
   g.U1 = pl->ruu_const ? nullptr : w.Ruu;
   g.V1 = w.ruu;
   g.g1 = pl->ruu_const ? -pl->ruu_value : -1.0;
+  g.band = ops->band_D;
   VGM_TRY(dgemm_nt(g, s));
   if (info) { info->gemm_calls += 1; info->kernel_launches += 2; }
   return VGM_OK;
@@ -530,6 +638,7 @@ static int state_sweep_level(const vgm_sweep_plan* pl, const vgm_operators* ops,
       g.N = l1 - l0; g.M = T; g.K = T;
       g.rowsA = pl->live_state + l0;
       g.alpha = 1.0;
+      g.band = ops->band_D;
       VGM_TRY(dgemm_nt(g, s));
       cnt.gemm += 1; cnt.launches += 1;
     }
@@ -545,7 +654,7 @@ static int state_sweep_level(const vgm_sweep_plan* pl, const vgm_operators* ops,
   }
   const int r0 = pl->level_ptr_host[lev], r1 = pl->level_ptr_host[lev + 1];
   int rc = pcg_solve(ops, pl->ruu_const, w.Ruu, w.Lambda, w.rhs, X, pl->slot_state, pl->slot_has_self,
-                     pl->level_slots + r0, r1 - r0, T, ld, opts, w.pcg, info, cnt, s);
+                     pl->level_slots + r0, r1 - r0, pl->n_hidden, T, ld, opts, w.pcg, info, cnt, s);
   if (info) {
     info->gemm_calls += cnt.gemm;
     info->kernel_launches += cnt.launches;
@@ -659,8 +768,8 @@ extern "C" int vgm_pcg_solve(const vgm_operators* ops, int ruu_const, const doub
   VGM_TRY(pcg_carve(ws, ws_bytes, n_hidden, T, ld, w));
   if (info) memset(info, 0, sizeof(*info));
   Counters cnt;
-  int r = pcg_solve(ops, ruu_const, Ruu, Lambda, rhs, X, slot_state, nullptr, rows, n_rows, T, ld, opts, w, info, cnt,
-                    (cudaStream_t)stream);
+  int r = pcg_solve(ops, ruu_const, Ruu, Lambda, rhs, X, slot_state, nullptr, rows, n_rows, n_hidden, T, ld, opts, w,
+                    info, cnt, (cudaStream_t)stream);
   if (info) { info->gemm_calls = cnt.gemm; info->kernel_launches = cnt.launches; }
   return r;
 }

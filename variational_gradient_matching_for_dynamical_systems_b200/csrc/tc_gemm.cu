@@ -1,41 +1,41 @@
-// tcgen05 / TMEM / TMA BF16 GEMM for the low-precision side of the solver (sm_100a).
+// tcgen05 / TMEM / TMA BF16 GEMM for the low-precision side of the mixed-precision solver (sm_100a).
 //
-//   acc[n][m] = sum_k A[n][k] * B[m][k]        A: [n_rows][lda] bf16 (compact rows, K-contiguous)
-//                                              B: [M][ldb]      bf16 (a T x T operator, K-contiguous)
-// A preconditioner only has to be a fixed SPD approximation of an inverse, so it is applied in
-// BF16 with FP32 accumulation on the 5th-generation tensor cores; the FP64 DMMA pipe is left to
-// the operator GEMM.  One persistent CTA per SM, warp-specialised:
-//   warp 0     TMA producer   (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring)
-//   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16; FP32 in TMEM)
-//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
-// Two 256-column TMEM accumulators are double-buffered so the epilogue of tile i overlaps the
+//   out[n][m] = sum_k A0[n][k] B0[m][k]  (+ A1[n][k] B0[m][k] + A0[n][k] B1[m][k])
+//       A*: [n_rows][lda] bf16, compact rows, K-contiguous  (search directions / residuals of the systems)
+//       B*: [M][ldb]      bf16, a T x T operator, K-contiguous (M = (cI-D)^T(cI-D) or the preconditioner G)
+// With both operands split into bf16 (hi, lo) pairs the three leading products give ~2^-16 relative
+// accuracy with FP32 accumulation -- enough for the correction solves of iterative refinement, whose
+// residuals stay in FP64 on the DMMA pipe (sweep.cu).  The operators of the hot path are numerically
+// banded (|B[m][k]| < 2^-64 max|B| beyond the band), so a column tile only visits the k-blocks inside
+// [m0 - band, m0 + BN + band).
+// One persistent CTA per SM, warp-specialised:
+//   warp 0     TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier ring; one stage = the A and B
+//                               k-blocks of every split part, loaded once and used by all three products)
+//   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16; FP32 in TMEM)
+//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> registers -> 128-byte row segments -> global)
+// Two 128-column TMEM accumulators are double-buffered so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Out-of-range rows / columns / K are zero-filled by TMA.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "vgm_common.cuh"
+#include "vgm_profile.cuh"
+#include "tc_gemm.cuh"
 
 namespace vgm {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2;
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-struct TcGemmArgs {
-  int M, K;                 // output columns, contraction length
-  int n_rows;               // host upper bound of active rows
-  const int* n_rows_dev;    // optional device-side count
-  const int* rows;          // compact row j -> physical row of the [.][ld] epilogue operands (null: identity)
-  int ld;                   // leading dimension of the epilogue operands
-  int mode;                 // epilogue selector
-  double* Z;                // MODE_Z: Z[row][m] = acc
-  const double* dotw;       //         dot_out[row*dot_ld + column_tile] = sum_m dotw[row][m] * acc
-  double* dot_out;
-  int dot_ld;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_UMMA_K = 16;
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_TILE_BYTES = 128 * TC_BK * 2;                 // one 128 x 64 bf16 operand tile (A or B part)
+constexpr int TC_TMEM_COLS = 2 * TC_BN;
+template <bool SPLIT>
+struct TcCfg {
+  static constexpr int PARTS = SPLIT ? 2 : 1;                  // (hi, lo) or hi only, for A and for B
+  static constexpr int STAGE_BYTES = 2 * PARTS * TC_TILE_BYTES;
+  static constexpr int STAGES = SPLIT ? 3 : 6;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
-enum { TC_MODE_Z = 0 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,40 +110,56 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
 
+struct TcMaps {
+  CUtensorMap a0, a1, b0, b1;
+};
+
+// k-block range of column tile ct
+__device__ __forceinline__ void tc_k_range(int ct, int K, int band, int& kb_lo, int& kb_hi) {
+  kb_lo = 0;
+  kb_hi = (K + TC_BK - 1) / TC_BK;
+  if (band > 0) {
+    const int m0 = ct * TC_BN;
+    kb_lo = max(0, m0 - band) / TC_BK;
+    kb_hi = min(kb_hi, (min(K, m0 + TC_BN + band) + TC_BK - 1) / TC_BK);
+  }
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcGemmArgs a) {
+tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
+  using Cfg = TcCfg<SPLIT>;
+  constexpr int STAGES = Cfg::STAGES, PARTS = Cfg::PARTS;
   extern __shared__ unsigned char tc_smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = smem;                                   // [STAGES][128][128B]
-  unsigned char* sB = smem + TC_STAGES * TC_A_BYTES;          // [STAGES][256][128B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  // stage layout: [A0][A1 if split][B0][B1 if split], 16 KB each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;                                  // [STAGES]
-  uint64_t* empty_bar = bars + TC_STAGES;                     // [STAGES]
-  uint64_t* tmem_full = bars + 2 * TC_STAGES;                 // [2]
-  uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;            // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+  uint64_t* empty_bar = bars + STAGES;                        // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;                    // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;               // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
+  const int n_rows = a.n_rows;
   const int row_tiles = (n_rows + TC_BM - 1) / TC_BM;
   const int col_tiles = (a.M + TC_BN - 1) / TC_BN;
   const int n_tiles = row_tiles * col_tiles;
-  const int k_blocks = (a.K + TC_BK - 1) / TC_BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 32 * TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation: 512 columns = two 128 x 256 FP32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(512));
+  if (warp == 1) {   // TMEM allocation: two 128 x 128 FP32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -158,12 +174,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int rt = tile / col_tiles, ct = tile % col_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        int kb_lo, kb_hi;
+        tc_k_range(ct, a.K, a.band, kb_lo, kb_hi);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-          tma_load_2d(sA + stage * TC_A_BYTES, &mapA, &full_bar[stage], kb * TC_BK, rt * TC_BM);
-          tma_load_2d(sB + stage * TC_B_BYTES, &mapB, &full_bar[stage], kb * TC_BK, ct * TC_BN);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(st, &maps.a0, &full_bar[stage], kb * TC_BK, rt * TC_BM);
+          if (SPLIT) tma_load_2d(st + TC_TILE_BYTES, &maps.a1, &full_bar[stage], kb * TC_BK, rt * TC_BM);
+          tma_load_2d(st + PARTS * TC_TILE_BYTES, &maps.b0, &full_bar[stage], kb * TC_BK, ct * TC_BN);
+          if (SPLIT) tma_load_2d(st + (PARTS + 1) * TC_TILE_BYTES, &maps.b1, &full_bar[stage], kb * TC_BK, ct * TC_BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -174,23 +195,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int ct = tile % col_tiles;
+        int kb_lo, kb_hi;
+        tc_k_range(ct, a.K, a.band, kb_lo, kb_hi);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * TC_BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);             // TMA landed A/B of this stage
+        uint32_t accumulate = 0;
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          mbar_wait(&full_bar[stage], phase);             // TMA landed this stage
           tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(sA + stage * TC_A_BYTES);
-          const uint64_t bdesc = make_sw128_desc(sB + stage * TC_B_BYTES);
+          unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+          const uint64_t a0 = make_sw128_desc(st);
+          const uint64_t b0 = make_sw128_desc(st + PARTS * TC_TILE_BYTES);
+          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
-            tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), TC_IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(tmem_d, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), TC_IDESC, accumulate);
+            accumulate = 1;
+          }
+          if (SPLIT) {
+            const uint64_t a1 = make_sw128_desc(st + TC_TILE_BYTES);
+            const uint64_t b1 = make_sw128_desc(st + (PARTS + 1) * TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              tc_mma_bf16(tmem_d, a1 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), TC_IDESC, 1u);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              tc_mma_bf16(tmem_d, a0 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), TC_IDESC, 1u);
           }
           tc_commit(&empty_bar[stage]);                   // frees the smem slot when the MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tmem_full[acc]);                       // accumulator complete -> epilogue
       }
@@ -205,41 +242,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int j = rt * TC_BM + q * 32 + lane;           // compact row handled by this thread
+      const int j = rt * TC_BM + q * 32 + lane;           // this thread's TMEM lane = compact row j
       const bool row_ok = j < n_rows;
-      const int prow = row_ok ? (a.rows ? a.rows[j] : j) : 0;
-      const size_t roff = (size_t)prow * a.ld;
+      float* __restrict__ orow = a.out + (size_t)(row_ok ? j : 0) * a.ldo;
       const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16);
-      double dsum = 0.0;
 #pragma unroll 1
       for (int c = 0; c < TC_BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);                          // warp-collective: executed by all lanes
         const int m0 = ct * TC_BN + c;
-        if (row_ok && m0 < a.M) {
-          if (m0 + 32 <= a.M) {
+        if (!row_ok || m0 >= a.M) continue;
+        if (m0 + 32 <= a.M) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const double z0 = (double)__uint_as_float(v[i]), z1 = (double)__uint_as_float(v[i + 1]);
-              *reinterpret_cast<double2*>(a.Z + roff + m0 + i) = make_double2(z0, z1);
-              if (a.dotw) {
-                const double2 w = *reinterpret_cast<const double2*>(a.dotw + roff + m0 + i);
-                dsum += w.x * z0 + w.y * z1;
-              }
-            }
-          } else {
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<uint4*>(orow + m0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (m0 + i < a.M) {
-                const double z = (double)__uint_as_float(v[i]);
-                a.Z[roff + m0 + i] = z;
-                if (a.dotw) dsum += a.dotw[roff + m0 + i] * z;
-              }
-            }
-          }
+          for (int i = 0; i < 32; ++i)
+            if (m0 + i < a.M) orow[m0 + i] = __uint_as_float(v[i]);
         }
       }
-      if (row_ok && a.dot_out) a.dot_out[(size_t)prow * a.dot_ld + ct] = dsum;
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
@@ -248,7 +270,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
   }
 }
 
@@ -284,43 +306,95 @@ static int make_bf16_map(CUtensorMap* map, const void* base, int rows, int cols,
   return VGM_OK;
 }
 
-int tc_gemm_dot_tiles(int M) { return ceil_div(M, TC_BN); }
-
-// A: [a_rows][lda] bf16 (compact), B: [M][ldb] bf16
-int tc_gemm(const void* A, int a_rows, int lda, const void* B, int ldb, const TcGemmArgs& args, cudaStream_t s) {
-  VGM_REQUIRE(A && B && args.M > 0 && args.K > 0 && args.n_rows >= 0, "tc_gemm arguments");
-  VGM_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0,
-              "tc_gemm operands must have 16-byte aligned rows");
-  if (args.n_rows == 0) return VGM_OK;
-  static int n_sm = 0;
+template <bool SPLIT>
+static int tc_launch(const TcMaps& maps, const TcGemmArgs& args, int n_sm, cudaStream_t s) {
+  using Cfg = TcCfg<SPLIT>;
   static bool attr = false;
   if (!attr) {
-    int dev = 0;
-    VGM_CUDA_OK(cudaGetDevice(&dev));
-    VGM_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    VGM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    VGM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  CUtensorMap mapA, mapB;
-  VGM_TRY(make_bf16_map(&mapA, A, a_rows, args.K, lda, TC_BM));
-  VGM_TRY(make_bf16_map(&mapB, B, args.M, args.K, ldb, TC_BN));
   const int tiles = ceil_div(args.n_rows, TC_BM) * ceil_div(args.M, TC_BN);
   const int grid = tiles < n_sm ? tiles : n_sm;
-  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(mapA, mapB, args);
+  tc_gemm_kernel<SPLIT><<<grid, TC_THREADS, Cfg::SMEM, s>>>(maps, args);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }
 
+int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
+  VGM_REQUIRE(args.A0 && args.B0 && args.out && args.M > 0 && args.K > 0 && args.n_rows >= 0, "tc_gemm arguments");
+  VGM_REQUIRE((args.A1 != nullptr) == (args.B1 != nullptr), "split needs both A1 and B1");
+  VGM_REQUIRE((args.lda % 8) == 0 && (args.ldb % 8) == 0 && (args.ldo % 4) == 0, "tc_gemm leading dimensions");
+  VGM_REQUIRE(((uintptr_t)args.A0 % 16) == 0 && ((uintptr_t)args.B0 % 16) == 0 && ((uintptr_t)args.A1 % 16) == 0 &&
+                  ((uintptr_t)args.B1 % 16) == 0 && ((uintptr_t)args.out % 16) == 0,
+              "tc_gemm operands must be 16-byte aligned");
+  if (args.n_rows == 0) return VGM_OK;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    VGM_CUDA_OK(cudaGetDevice(&dev));
+    VGM_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool split = args.A1 != nullptr;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  VGM_TRY(make_bf16_map(&maps.a0, args.A0, args.n_rows, args.K, args.lda, TC_BM));
+  VGM_TRY(make_bf16_map(&maps.b0, args.B0, args.M, args.K, args.ldb, TC_BN));
+  if (split) {
+    VGM_TRY(make_bf16_map(&maps.a1, args.A1, args.n_rows, args.K, args.lda, TC_BM));
+    VGM_TRY(make_bf16_map(&maps.b1, args.B1, args.M, args.K, args.ldb, TC_BN));
+  }
+  // executed MMA flops (band) and compulsory HBM bytes (A parts once, FP32 output once)
+  double ksum = 0.0;
+  for (int m0 = 0; m0 < args.M; m0 += TC_BN)
+    ksum += args.band > 0 ? (double)(min(args.K, m0 + TC_BN + args.band) - max(0, m0 - args.band)) : (double)args.K;
+  const double flops = 2.0 * args.n_rows * TC_BN * ksum * (split ? 3.0 : 1.0);
+  const double bytes = (double)args.n_rows * args.K * 2.0 * (split ? 2.0 : 1.0) + (double)args.n_rows * args.M * 4.0;
+  ProfScope prof(PROF_TCGEMM, flops, bytes, s);
+  return split ? tc_launch<true>(maps, args, n_sm, s) : tc_launch<false>(maps, args, n_sm, s);
+}
+
+__global__ void f64_to_bf16_kernel(const double* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __double2bfloat16(in[i]);
+}
+// hi = bf16(x), lo = bf16(x - hi): out[0..n) = hi plane, out[n..2n) = lo plane
+__global__ void f64_split_bf16_kernel(const double* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double x = in[i];
+    const __nv_bfloat16 hi = __double2bfloat16(x);
+    out[i] = hi;
+    out[n + i] = __double2bfloat16(x - (double)__bfloat162float(hi));
+  }
+}
+
 }  // namespace vgm
 
-// Test/bench entry: Z[rows[j]] = A[j] . B^T with A, B bf16 (device), Z fp64; optional dots.
-extern "C" int vgm_tc_gemm_bf16(const void* A_bf16, int a_rows, int lda, const void* B_bf16, int M, int K, int ldb,
-                                int n_rows, const int* n_rows_dev, const int* rows, double* Z, int ldz,
-                                const double* dotw, double* dot_out, int dot_ld, vgm_stream_t stream) {
+extern "C" int vgm_tc_gemm_bf16(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1,
+                                int M, int K, int ldb, int band, float* out, int ldo, vgm_stream_t stream) {
   vgm::TcGemmArgs a;
   memset(&a, 0, sizeof(a));
-  a.M = M; a.K = K; a.n_rows = n_rows; a.n_rows_dev = n_rows_dev; a.rows = rows; a.ld = ldz;
-  a.mode = vgm::TC_MODE_Z; a.Z = Z; a.dotw = dotw; a.dot_out = dot_out; a.dot_ld = dot_ld;
-  VGM_REQUIRE(Z && (ldz % 2) == 0, "Z");
-  return vgm::tc_gemm(A_bf16, a_rows, lda, B_bf16, ldb, a, (cudaStream_t)stream);
+  a.n_rows = n_rows; a.M = M; a.K = K; a.band = band;
+  a.A0 = A0; a.A1 = A1; a.lda = lda; a.B0 = B0; a.B1 = B1; a.ldb = ldb; a.out = out; a.ldo = ldo;
+  return vgm::tc_gemm(a, (cudaStream_t)stream);
+}
+
+// G (fp64, [rows][ld]) -> bf16 copy with the same shape; used once per preconditioner.
+extern "C" int vgm_convert_bf16(const double* in, void* out_bf16, int rows, int ld, vgm_stream_t stream) {
+  VGM_REQUIRE(in && out_bf16 && rows > 0 && ld > 0, "convert arguments");
+  const size_t n = (size_t)rows * ld;
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  vgm::f64_to_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, n);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+// M (fp64, [rows][ld]) -> [2][rows][ld] bf16 (hi, lo) planes.
+extern "C" int vgm_split_bf16(const double* in, void* out_bf16x2, int rows, int ld, vgm_stream_t stream) {
+  VGM_REQUIRE(in && out_bf16x2 && rows > 0 && ld > 0, "split arguments");
+  const size_t n = (size_t)rows * ld;
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  vgm::f64_split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16x2, n);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
 }

@@ -1,0 +1,25 @@
+// Argument block of the tcgen05 BF16 GEMM (tc_gemm.cu) shared with the solver (sweep.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace vgm {
+
+// out[j][m] = sum_k A0[j][k] B0[m][k]  (+ A1 B0^T + A0 B1^T when split), raw FP32 accumulators.
+struct TcGemmArgs {
+  int n_rows;               // rows of A* and out (compact)
+  int M, K;                 // output columns, contraction length
+  int band;                 // B*[m][k] == 0 for |m - k| > band (<= 0: dense)
+  const void* A0;           // [n_rows][lda] bf16
+  const void* A1;           // optional low part of A (split)
+  int lda;
+  const void* B0;           // [M][ldb] bf16
+  const void* B1;           // optional low part of B (split)
+  int ldb;
+  float* out;               // [n_rows][ldo] fp32
+  int ldo;
+};
+
+int tc_gemm(const TcGemmArgs& args, cudaStream_t s);
+
+}  // namespace vgm

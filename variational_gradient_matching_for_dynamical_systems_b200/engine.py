@@ -49,7 +49,23 @@ class Operators:
         self.M_c = None
         self.G = None
         self.G_bf16 = None
+        self.M_bf16x2 = None
         self.G_shift = None
+        self.band_M = self.band_G = 0
+        self.band_D = self.band_of(self.D)
+
+    # |B[i][j]| <= 2^-64 max|B| beyond the band: dropping it perturbs any product by less than half an
+    # ulp of its normwise rounding error, so the banded GEMMs stay FP64-exact in the backward sense.
+    EXACT_BAND = 2.0 ** -64
+
+    def band_of(self, B, rel=None):
+        """Half band width of a T x T operator on the device (vgm_band_halfwidth); 0 = treat as dense."""
+        out = C.c_int(0)
+        _lib.check(_lib.load().vgm_band_halfwidth(B.data_ptr(), self.T, self.T, self.ld,
+                                                   self.EXACT_BAND if rel is None else rel, C.byref(out),
+                                                   _lib.stream_ptr()))
+        band = int(out.value)
+        return band if 0 < band < self.T - 64 else 0
 
     def _pad(self, M):
         out = torch.zeros((self.T, self.ld), dtype=torch.float64, device=self.dev)
@@ -73,6 +89,7 @@ class Operators:
         g.alpha = 1.0
         _lib.check(lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
         self.M, self.M_c = M, c
+        self.band_M = self.band_of(M)
         self.G = None
         return M
 
@@ -89,9 +106,14 @@ class Operators:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
         _lib.check(lib.vgm_spd_inverse(S.data_ptr(), T, ld, G.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr()))
         self.G, self.G_shift = G, float(shift)
-        # BF16 copy for the tensor-core application of the preconditioner
+        # low-precision operands of the mixed-precision solver: bf16 G (a preconditioner only has to be a
+        # fixed SPD approximation, so entries below the bf16 resolution are dropped as well) and the
+        # bf16 (hi, lo) split of M
         self.G_bf16 = torch.zeros((T, ld), dtype=torch.bfloat16, device=self.dev)
         _lib.check(lib.vgm_convert_bf16(G.data_ptr(), self.G_bf16.data_ptr(), T, ld, _lib.stream_ptr()))
+        self.band_G = self.band_of(G, rel=2.0 ** -9)
+        self.M_bf16x2 = torch.zeros((2, T, ld), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(lib.vgm_split_bf16(self.M.data_ptr(), self.M_bf16x2.data_ptr(), T, ld, _lib.stream_ptr()))
         return G
 
 
@@ -164,11 +186,20 @@ class VGMEngine:
     hidden : state indices to update, in the reference's order (proxies...py:175-179,195)
     theta_mode : 'reference' plugs the literal ``theta_literal`` (default [8.0], the value
         hard-coded at proxies...py:211) into R_uk, r_uk; 'proxy' plugs the current estimate.
+    solver : 'mixed' = FP64 residuals on the DMMA pipe + FP32 PCG corrections whose operator products run
+        on the tcgen05 tensor cores (bf16-split operands); 'pcg' = FP64 preconditioned CG only;
+        'auto' = 'mixed' whenever the model allows it (R_uu constant, T >= MIXED_MIN_T).
     """
+    MIXED_MIN_T = 64
+    # preconditioner S G S of the mixed-precision solver: G = (M + SHIFT_FRAC mean(Lambda) I)^-1,
+    # S = diag sqrt((shift + c) / (Lambda + c)), c = SCALE_FRAC mean(Lambda); spec(S G S A) then has a
+    # condition number of ~6-7 instead of ~20 for the plain shifted inverse (Lorenz96, C3/C5 of BASELINE.json)
+    SHIFT_FRAC, SCALE_FRAC = 0.55, 1.5
 
     def __init__(self, model: OdeModel, D, A=None, hidden=None, couplings=None, schedule="reference",
                  theta_mode="reference", theta_literal=(8.0,), tol=1e-13, max_iter=0, check_every=8,
-                 precondition=True, precond_dtype="bf16", prefer_builtin=True, device=None, problem=None):
+                 precondition=True, solver="auto", inner_iters=10, prefer_builtin=True,
+                 device=None, problem=None):
         self.lib = _lib.load()
         self.dev = device or _lib.require_cuda()
         self.model = model
@@ -192,10 +223,15 @@ class VGMEngine:
             raise TypeError("the reference plugs the literal [8] into R_uk, r_uk (proxies...py:211); a model with %d "
                             "parameters needs theta_mode='proxy' or a theta_literal of that length" % self.p)
         self.precondition = bool(precondition)
-        if precond_dtype not in ("bf16", "f64"):
-            raise ValueError("precond_dtype must be 'bf16' or 'f64'")
-        self.precond_dtype = precond_dtype
-        self.opts = _lib.SolverOpts(tol, max_iter, check_every)
+        if solver not in ("auto", "mixed", "pcg"):
+            raise ValueError("solver must be 'auto', 'mixed' or 'pcg'")
+        # 'mixed': FP64 residuals + FP32/bf16-split tensor-core corrections (needs a shared system matrix, i.e.
+        # R_uu constant, and the preconditioner); 'pcg': FP64 preconditioned CG on the DMMA pipe only
+        can_mix = bool(self.plan.c.ruu_const) and self.precondition and self.T >= self.MIXED_MIN_T
+        if solver == "mixed" and not can_mix:
+            raise ValueError("solver='mixed' needs constant R_uu, precondition=True and T >= %d" % self.MIXED_MIN_T)
+        self.solver = "mixed" if (solver in ("auto", "mixed") and can_mix) else "pcg"
+        self.opts = _lib.SolverOpts(tol, max_iter, check_every, int(inner_iters))
         self.X = torch.zeros((self.K, self.ld), dtype=torch.float64, device=self.dev)
         self.DX = torch.zeros_like(self.X)
         self.theta = torch.zeros(max(self.p, 1), dtype=torch.float64, device=self.dev)
@@ -203,8 +239,10 @@ class VGMEngine:
         self.stats = torch.zeros(self.p + self.p * self.p, dtype=torch.float64, device=self.dev)
         self._cops = _lib.Operators()
         self._cops.D, self._cops.DT = self.ops.D.data_ptr(), self.ops.DT.data_ptr()
+        self._cops.band_D = self.ops.band_D
         if self.plan.c.ruu_const:
             self._cops.M = self.ops.ensure_shared_M(self.plan.c.ruu_value).data_ptr()
+            self._cops.band_M = self.ops.band_M
         self._mt = _lib.ModelTables()
         self._mt.n_states, self._mt.n_odes, self._mt.n_param = self.K, problem.n_stats_odes, self.p
         self._mt.ode_class = self.tables["ode_class"].data_ptr()
@@ -245,6 +283,7 @@ class VGMEngine:
         if not (self.precondition and self.plan.c.ruu_const) or self.plan.n_hidden == 0:
             self._cops.G = None
             self._cops.G_bf16 = None
+            self._cops.M_bf16x2 = None
             return
         if self.ops.G is None:
             # shift = mean of Lambda over all hidden states/time points of the current proxy
@@ -258,12 +297,18 @@ class VGMEngine:
                                                    self.DX.data_ptr(), self.theta_star.data_ptr(), lam.data_ptr(),
                                                    tmp[0].data_ptr(), tmp[1].data_ptr(), None, rlive.data_ptr(),
                                                    _lib.stream_ptr()))
-            shift = float(lam[:, :self.T].mean().item())
-            if not np.isfinite(shift) or shift <= 0:
-                shift = 1.0
-            self.ops.ensure_preconditioner(shift)
+            lam_mean = float(lam[:, :self.T].mean().item())
+            if not np.isfinite(lam_mean) or lam_mean <= 0:
+                lam_mean = 1.0
+            self.lam_mean = lam_mean
+            self.ops.ensure_preconditioner((self.SHIFT_FRAC if self.solver == "mixed" else 1.0) * lam_mean)
+        mixed = self.solver == "mixed"
         self._cops.G = self.ops.G.data_ptr()
-        self._cops.G_bf16 = self.ops.G_bf16.data_ptr() if self.precond_dtype == "bf16" else None
+        self._cops.G_bf16 = self.ops.G_bf16.data_ptr() if mixed else None
+        self._cops.M_bf16x2 = self.ops.M_bf16x2.data_ptr() if mixed else None
+        self._cops.G_shift = self.ops.G_shift
+        self._cops.precond_c = self.SCALE_FRAC * self.ops.G_shift / self.SHIFT_FRAC if mixed else 0.0
+        self._cops.band_G = self.ops.band_G
 
     def _set_theta_star(self, theta_star=None):
         if theta_star is not None:
@@ -281,6 +326,7 @@ class VGMEngine:
         g.lda = g.ldb = g.ldc = self.ld
         g.N, g.M, g.K = self.K, self.T, self.T
         g.alpha = 1.0
+        g.band = self.ops.band_D
         _lib.check(self.lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
 
     def param_stats(self):

@@ -34,7 +34,7 @@ class settings:
     theta_mode = "reference"        # 'reference' | 'proxy'
     theta_literal = 8.0             # proxies...py:211
     tol = 1e-13                     # relative residual of the per-state solves
-    precond_dtype = "bf16"
+    solver = "auto"
     schedule = "reference"          # 'reference' | 'colour' (opt-in parallel multi-colour schedule)
     _warned = False
 
@@ -59,7 +59,7 @@ def _model_of(locally_linear_odes):
 
 def _engine(model, D, A, hidden, couplings, theta_mode):
     key = (id(model), _fingerprint(D), tuple(hidden), None if couplings is None else id(couplings), theta_mode,
-           settings.tol, settings.precond_dtype, settings.schedule)
+           settings.tol, settings.solver, settings.schedule)
     eng = _engines.get(key)
     if eng is None:
         if len(_engines) > 8:
@@ -67,7 +67,7 @@ def _engine(model, D, A, hidden, couplings, theta_mode):
         ops = Operators(D, A)
         literal = tuple([float(settings.theta_literal)] * model.p)
         eng = VGMEngine(model, ops, None, hidden=hidden, couplings=couplings, theta_mode=theta_mode,
-                        theta_literal=literal, tol=settings.tol, precond_dtype=settings.precond_dtype,
+                        theta_literal=literal, tol=settings.tol, solver=settings.solver,
                         schedule=settings.schedule)
         _engines[key] = eng
     return eng
