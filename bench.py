@@ -344,7 +344,8 @@ def native_arm(args):
                        if core.solver == "mixed" else
                        ("FP64 PCG (tol %g) on the DMMA pipe, preconditioner %s" %
                         (args.tol, "none" if args.no_precondition else "(M+shift I)^-1")),
-                       "bands": {"D": core.ops.band_D, "M": core.ops.band_M, "G_bf16": core.ops.band_G},
+                       "bands": {"D": core.ops.band_D, "M": core.ops.band_M, "M_bf16": core.ops.band_M_lp,
+                                 "G_bf16": core.ops.band_G},
                        "parallelism": "state-block x%d" % world,
                        "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
                              (n_hidden_local * core.ld * 8 / 1e6),

@@ -189,7 +189,10 @@ typedef struct {
                            corrections by FP32 PCG whose operator products run on the tcgen05 tensor cores  */
   double G_shift;       /* the shift G was built with                                                          */
   double precond_c;     /* > 0: the preconditioner is S G S with S = diag sqrt((G_shift + c) / (Lambda + c))    */
-  int band_D, band_M, band_G; /* half band widths of D (and D^T), M and G (vgm_band_halfwidth); <= 0: dense     */
+  int band_D, band_M;   /* half band widths of D (and D^T) and M at the FP64-exact threshold 2^-64
+                           (vgm_band_halfwidth); <= 0: dense                                                  */
+  int band_M_lp, band_G; /* half band widths used on the low-precision side: M at ~2^-20 (the bf16-split product
+                           resolves 2^-16), G at ~2^-7 (a preconditioner only has to stay SPD); <= 0: dense   */
 } vgm_operators;
 int vgm_convert_bf16(const double* in, void* out_bf16, int rows, int ld, vgm_stream_t stream);
 int vgm_split_bf16(const double* in, void* out_bf16x2, int rows, int ld, vgm_stream_t stream);

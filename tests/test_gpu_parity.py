@@ -168,7 +168,8 @@ def test_tcgen05_gemm_matches_fp32_reference(pkg, n, T, band, split):
     else:
         ref_ops = d(Phi) @ d(Bhi).t()
     scale = float(ref_ops.abs().max())
-    assert float((d(out[:, :T]) - ref_ops).abs().max()) / scale < 2e-6
+    # fp32 accumulation over K (x3 when split) terms of random sign: ~sqrt(K) * 2^-24 relative to the row scale
+    assert float((d(out[:, :T]) - ref_ops).abs().max()) / scale < 2e-5
     if split:
         exact = d(P) @ d(Bm).t()
         assert float((d(out[:, :T]) - exact).abs().max()) / scale < 1e-4

@@ -57,7 +57,7 @@ class SweepPlan(C.Structure):
 class Operators(C.Structure):
     _fields_ = [("D", c_dp), ("DT", c_dp), ("M", c_dp), ("G", c_dp), ("G_bf16", c_dp), ("M_bf16x2", c_dp),
                 ("G_shift", C.c_double), ("precond_c", C.c_double),
-                ("band_D", C.c_int), ("band_M", C.c_int), ("band_G", C.c_int)]
+                ("band_D", C.c_int), ("band_M", C.c_int), ("band_M_lp", C.c_int), ("band_G", C.c_int)]
 
 
 class SolverOpts(C.Structure):

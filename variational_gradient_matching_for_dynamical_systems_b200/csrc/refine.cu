@@ -98,25 +98,29 @@ ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __rest
   if (threadIdx.x == 0) b.sigma[j] = sig;
 }
 
+// REG: the row fits one pass (T <= 4 * IR_THREADS), so z / (p, q) stay in registers and the kernel needs no
+// dynamic shared memory -- its CTAs then co-reside with the persistent tcgen05 GEMM of the other row chunk.
+template <bool REG>
 __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, int T, int ld, int first) {
-  extern __shared__ float ir_sm[];       // z of this row
+  extern __shared__ float ir_sm[];       // z of this row (!REG)
   __shared__ double red[40];
   const int j = blockIdx.x;
   const size_t o = (size_t)j * ld;
   double part = 0.0;
+  float4 zreg = make_float4(0.f, 0.f, 0.f, 0.f);
   IR_ROW_LOOP(i, T) {
     const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
     const float4 sv = ld_bf4(b.s16 + o + i);
     const float4 r = *reinterpret_cast<const float4*>(b.r32 + o + i);
     const float4 z = make_float4(sv.x * acc.x, sv.y * acc.y, sv.z * acc.z, sv.w * acc.w);
-    *reinterpret_cast<float4*>(ir_sm + i) = z;
+    if (REG) zreg = z; else *reinterpret_cast<float4*>(ir_sm + i) = z;
     part += (double)r.x * z.x + (double)r.y * z.y + (double)r.z * z.z + (double)r.w * z.w;
   }
   const double rz_new = block_sum(part, red);
   const double rz_old = first ? 0.0 : b.rz[j];
   const float beta = (first || !(rz_old > 0.0)) ? 0.f : (float)(rz_new / rz_old);
   IR_ROW_LOOP(i, T) {
-    float4 p = *reinterpret_cast<const float4*>(ir_sm + i);
+    float4 p = REG ? zreg : *reinterpret_cast<const float4*>(ir_sm + i);
     if (!first) {
       const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
       p.x += beta * (h.x + l.x); p.y += beta * (h.y + l.y); p.z += beta * (h.z + l.z); p.w += beta * (h.w + l.w);
@@ -128,14 +132,16 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, int T, int 
   if (threadIdx.x == 0) b.rz[j] = rz_new;
 }
 
+template <bool REG>
 __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, int T, int ld, int last) {
-  extern __shared__ float ir_sm[];       // p and q of this row
+  extern __shared__ float ir_sm[];       // p and q of this row (!REG)
   __shared__ double red[40];
   float* sp = ir_sm;
   float* sq = ir_sm + ((T + 3) & ~3);
   const int j = blockIdx.x;
   const size_t o = (size_t)j * ld;
   double part = 0.0;
+  float4 preg = make_float4(0.f, 0.f, 0.f, 0.f), qreg = preg;
   IR_ROW_LOOP(i, T) {
     const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
     const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
@@ -143,15 +149,17 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, int T, i
     const float4 p = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
     const float4 q = make_float4(fmaf(lam.x, p.x, acc.x), fmaf(lam.y, p.y, acc.y), fmaf(lam.z, p.z, acc.z),
                                  fmaf(lam.w, p.w, acc.w));
-    *reinterpret_cast<float4*>(sp + i) = p;
-    *reinterpret_cast<float4*>(sq + i) = q;
+    if (REG) { preg = p; qreg = q; } else {
+      *reinterpret_cast<float4*>(sp + i) = p;
+      *reinterpret_cast<float4*>(sq + i) = q;
+    }
     part += (double)p.x * q.x + (double)p.y * q.y + (double)p.z * q.z + (double)p.w * q.w;
   }
   const double pq = block_sum(part, red);
   const float alpha = (pq > 0.0) ? (float)(b.rz[j] / pq) : 0.f;
   IR_ROW_LOOP(i, T) {
-    const float4 p = *reinterpret_cast<const float4*>(sp + i);
-    const float4 q = *reinterpret_cast<const float4*>(sq + i);
+    const float4 p = REG ? preg : *reinterpret_cast<const float4*>(sp + i);
+    const float4 q = REG ? qreg : *reinterpret_cast<const float4*>(sq + i);
     float4 d = *reinterpret_cast<const float4*>(b.d32 + o + i);
     d.x = fmaf(alpha, p.x, d.x); d.y = fmaf(alpha, p.y, d.y); d.z = fmaf(alpha, p.z, d.z); d.w = fmaf(alpha, p.w, d.w);
     *reinterpret_cast<float4*>(b.d32 + o + i) = d;
@@ -194,7 +202,8 @@ int ir_dir(const IrBuf& b, int n, int T, int ld, int first, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   // reads acc32 4, s16 2, r32 4, (p_hi, p_lo 4); writes p_hi, p_lo 4
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * (first ? 14.0 : 18.0), s);
-  ir_dir_kernel<<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, first);
+  if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, T, ld, first);
+  else ir_dir_kernel<false><<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, first);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }
@@ -203,7 +212,8 @@ int ir_update(const IrBuf& b, int n, int T, int ld, int last, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4, s16 2); writes d32 4, (r32 4, rsb 2)
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * (last ? 20.0 : 32.0), s);
-  ir_update_kernel<<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, last);
+  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, T, ld, last);
+  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, last);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }

@@ -13,6 +13,7 @@
 // read) are reproduced by solving dependency levels in order and patching rhs with the freshly
 // updated D x_k between levels.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "vgm_common.cuh"
 #include "vgm_profile.cuh"
@@ -287,6 +288,7 @@ static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, Pcg
 struct Counters {
   int gemm = 0, launches = 0;
 };
+static const bool g_debug = getenv("VGM_DEBUG") != nullptr;
 
 // Q = Op P (+ Lambda o P), partial dots p.q -> pq_part
 static int apply_operator(const vgm_operators* ops, int ruu_const, const double* Ruu, const double* Lambda, CgBuf& cb,
@@ -400,13 +402,14 @@ __global__ void ir_prep_kernel(CgBuf cb, const double* __restrict__ rhs, const d
 }
 
 // rr = ||r||^2 from the residual GEMM's partial dots; convergence test of the outer iteration.
-__global__ void ir_check_kernel(CgBuf cb, const int* __restrict__ act, int n_tiles, double tol2, int outer, int inner) {
+__global__ void ir_check_kernel(CgBuf cb, const int* __restrict__ act, int n_tiles, int dot_ld, double tol2, int outer,
+                                int inner) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *cb.n_act) return;
   const int slot = act[j];
   if (cb.done[slot]) return;
   double rr = 0.0;
-  for (int i = 0; i < n_tiles; ++i) rr += cb.pq_part[(size_t)slot * n_tiles + i];
+  for (int i = 0; i < n_tiles; ++i) rr += cb.pq_part[(size_t)slot * dot_ld + i];
   cb.rr[slot] = rr;
   cb.iters[slot] = outer * inner;
   if (rr <= tol2 * cb.bb[slot]) cb.done[slot] = 1;
@@ -418,6 +421,50 @@ __global__ void ir_check_kernel(CgBuf cb, const int* __restrict__ act, int n_til
 //                         tcgen05 GEMM (3 products, ~2^-16) and the preconditioner S G S (G = (M + shift I)^-1
 //                         in bf16, S the diagonal scaling of vgm_operators.precond_c).
 // Each correction contracts the error by ~1e-3..1e-4, so 4-5 FP64 GEMMs replace the ~60 of FP64 PCG.
+// Large levels are split into two independent row chunks driven on two streams: the tensor-core GEMMs of
+// one chunk are bound by L2->SMEM traffic, the vector kernels of the other by HBM, so they overlap.
+struct IrChunk {
+  int row0 = 0, n_rows = 0;        // slice of the level's row list
+  int cur = 0, n_upper = 0;
+  int* act_buf[2] = {nullptr, nullptr};
+  const int* act = nullptr;
+  int* n_act = nullptr;            // device: [0] current count, [1] scratch
+  IrBuf ir;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev = nullptr;
+  volatile int* host_cnt = nullptr;  // pinned
+  bool finished = false;
+};
+
+struct IrAsync {                   // created once, kept for the life of the process
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr}, fork = nullptr, join = nullptr;
+  int* host_cnt = nullptr;         // pinned, 2 x 16 ints
+};
+static IrAsync g_ir_async;
+
+static int ir_async_init() {
+  IrAsync& a = g_ir_async;
+  if (a.side) return VGM_OK;
+  VGM_CUDA_OK(cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) VGM_CUDA_OK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
+  VGM_CUDA_OK(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+  VGM_CUDA_OK(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+  VGM_CUDA_OK(cudaHostAlloc((void**)&a.host_cnt, 32 * sizeof(int), cudaHostAllocDefault));
+  return VGM_OK;
+}
+
+static IrBuf ir_view(const IrBuf& b, int row0, int ld) {
+  IrBuf v = b;
+  const size_t o = (size_t)row0 * ld;
+  v.r32 += o; v.d32 += o; v.acc32 += o; v.lam32 += o;
+  v.p_hi += o; v.p_lo += o; v.rsb += o; v.s16 += o;
+  v.sigma += row0; v.rz += row0;
+  return v;
+}
+
+constexpr int IR_CHUNK_MIN_ROWS = 4096;   // below this a level runs as one chunk on the caller's stream
+
 static int ir_solve(const vgm_operators* ops, const double* Lambda, const double* rhs, double* X,
                     const int* slot_state, const int* slot_has_self, const int* rows, int n_rows, int T, int ld,
                     const vgm_solver_opts* opts, PcgWs& w, vgm_sweep_info* info, Counters& cnt, cudaStream_t s) {
@@ -425,68 +472,119 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
   const int max_outer = (opts && opts->max_iter > 0) ? opts->max_iter : 30;
   const int inner = (opts && opts->inner_iters > 0) ? opts->inner_iters : 10;
   CgBuf& cb = w.cb;
-  IrBuf& ir = w.ir;
   const int th = row_threads(T);
   const __nv_bfloat16* M_hi = (const __nv_bfloat16*)ops->M_bf16x2;
   const __nv_bfloat16* M_lo = M_hi + (size_t)T * ld;
+  VGM_TRY(ir_async_init());
+  IrAsync& as = g_ir_async;
+  const int dot_ld = ceil_div(T, 64);                    // row stride of pq_part (its allocation bound)
 
-  VGM_CUDA_OK(cudaMemcpyAsync(cb.act[0], rows, (size_t)n_rows * sizeof(int), cudaMemcpyDeviceToDevice, s));
-  cg_set_count_kernel<<<1, 1, 0, s>>>(cb.n_act, n_rows);
-  int cur = 0;
-  const int* act = cb.act[0];
-  {
-    ProfScope prof(PROF_VEC, 0.0, (double)n_rows * T * 24.0, s);
-    ir_prep_kernel<<<n_rows, th, 0, s>>>(cb, rhs, Lambda, X, slot_state, slot_has_self, act, T, ld);
-    cg_gather_x_kernel<<<n_rows, th, 0, s>>>(X, slot_state, act, cb.n_act, T, ld, cb.P);
+  const int n_chunks = (n_rows >= 2 * IR_CHUNK_MIN_ROWS) ? 2 : 1;
+  IrChunk ch[2];
+  for (int c = 0; c < n_chunks; ++c) {
+    IrChunk& k = ch[c];
+    // chunk boundaries on multiples of 128 rows (whole GEMM row tiles)
+    const int half = ((n_rows / 2 + 127) / 128) * 128;
+    k.row0 = (c == 0) ? 0 : half;
+    k.n_rows = (n_chunks == 1) ? n_rows : (c == 0 ? half : n_rows - half);
+    k.act_buf[0] = cb.act[0] + k.row0;
+    k.act_buf[1] = cb.act[1] + k.row0;
+    k.n_act = cb.n_act + 4 * c;
+    k.ir = ir_view(w.ir, k.row0, ld);
+    k.st = (c == 0) ? s : as.side;
+    k.ev = as.ev[c];
+    k.host_cnt = as.host_cnt + 16 * c;
+    k.n_upper = k.n_rows;
+    k.act = k.act_buf[0];
   }
-  VGM_LAUNCH_OK();
-  cnt.launches += 4;
-
-  int n_upper = n_rows;
-  for (int outer = 0; outer <= max_outer && n_upper > 0; ++outer) {
-    // R = rhs - P M^T - Lambda o P, squared row norms -> pq_part
-    cb.n_tiles = gemm_dot_tiles(T, n_upper);
-    vgm_gemm_args g;
-    memset(&g, 0, sizeof(g));
-    g.A = cb.P; g.B = ops->M; g.C = cb.R;
-    g.lda = g.ldb = g.ldc = ld;
-    g.N = n_upper; g.M = T; g.K = T;
-    g.rowsA = act; g.rowsC = act; g.n_rows_dev = cb.n_act;
-    g.alpha = -1.0; g.beta = 1.0; g.C0 = rhs;
-    g.U1 = Lambda; g.V1 = cb.P; g.g1 = -1.0;
-    g.dotw = cb.R; g.dot_out = cb.pq_part; g.dot_ld = cb.n_tiles;
-    g.band = ops->band_M;
-    VGM_TRY(dgemm_nt(g, s));
-    ir_check_kernel<<<ceil_div(n_upper, 256), 256, 0, s>>>(cb, act, cb.n_tiles, tol * tol, outer, inner);
-    VGM_LAUNCH_OK();
-    cnt.gemm += 1; cnt.launches += 2;
-    VGM_TRY(compact_and_poll(cb, cur, act, n_upper, cnt, s));
-    if (n_upper == 0 || outer == max_outer) break;
-
-    const int n = n_upper;
-    VGM_TRY(ir_inner_init(ir, cb.R, Lambda, cb.rr, act, n, T, ld, ops->G_shift, ops->precond_c, s));
-    TcGemmArgs tg;
-    memset(&tg, 0, sizeof(tg));
-    tg.n_rows = n; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = ir.acc32; tg.ldo = ld;
-    TcGemmArgs tp = tg;                                   // z' = (s o r) G^T
-    tp.A0 = ir.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
-    TcGemmArgs to = tg;                                   // q' = p M^T (bf16 split)
-    to.A0 = ir.p_hi; to.A1 = ir.p_lo; to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M;
-    VGM_TRY(tc_gemm(tp, s));
-    VGM_TRY(ir_dir(ir, n, T, ld, 1, s));
-    cnt.launches += 3; cnt.gemm += 1;
-    for (int it = 0; it < inner; ++it) {
-      const int last = (it == inner - 1) ? 1 : 0;
-      VGM_TRY(tc_gemm(to, s));
-      VGM_TRY(ir_update(ir, n, T, ld, last, s));
-      cnt.launches += 2; cnt.gemm += 1;
-      if (last) break;
-      VGM_TRY(tc_gemm(tp, s));
-      VGM_TRY(ir_dir(ir, n, T, ld, 0, s));
-      cnt.launches += 2; cnt.gemm += 1;
+  if (n_chunks > 1) {
+    VGM_CUDA_OK(cudaEventRecord(as.fork, s));
+    VGM_CUDA_OK(cudaStreamWaitEvent(as.side, as.fork, 0));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    IrChunk& k = ch[c];
+    CgBuf cbk = cb;
+    cbk.n_act = k.n_act;
+    VGM_CUDA_OK(cudaMemcpyAsync(k.act_buf[0], rows + k.row0, (size_t)k.n_rows * sizeof(int), cudaMemcpyDeviceToDevice, k.st));
+    cg_set_count_kernel<<<1, 1, 0, k.st>>>(k.n_act, k.n_rows);
+    {
+      ProfScope prof(PROF_VEC, 0.0, (double)k.n_rows * T * 24.0, k.st);
+      ir_prep_kernel<<<k.n_rows, th, 0, k.st>>>(cbk, rhs, Lambda, X, slot_state, slot_has_self, k.act, T, ld);
+      cg_gather_x_kernel<<<k.n_rows, th, 0, k.st>>>(X, slot_state, k.act, k.n_act, T, ld, cb.P);
     }
-    VGM_TRY(ir_finish(ir, cb.P, X, slot_state, act, n, T, ld, s));
-    cnt.launches += 1;
+    VGM_LAUNCH_OK();
+    cnt.launches += 4;
+  }
+
+  for (int outer = 0; outer <= max_outer; ++outer) {
+    // --- FP64 residual, convergence test, compaction; the new count travels to pinned host memory ---
+    for (int c = 0; c < n_chunks; ++c) {
+      IrChunk& k = ch[c];
+      if (k.finished) continue;
+      CgBuf cbk = cb;
+      cbk.n_act = k.n_act;
+      const int n_tiles = gemm_dot_tiles(T, k.n_upper);
+      vgm_gemm_args g;
+      memset(&g, 0, sizeof(g));
+      g.A = cb.P; g.B = ops->M; g.C = cb.R;
+      g.lda = g.ldb = g.ldc = ld;
+      g.N = k.n_upper; g.M = T; g.K = T;
+      g.rowsA = k.act; g.rowsC = k.act; g.n_rows_dev = k.n_act;
+      g.alpha = -1.0; g.beta = 1.0; g.C0 = rhs;
+      g.U1 = Lambda; g.V1 = cb.P; g.g1 = -1.0;
+      g.dotw = cb.R; g.dot_out = cb.pq_part; g.dot_ld = dot_ld;   // fixed stride: chunks may tile differently
+      g.band = ops->band_M;
+      VGM_TRY(dgemm_nt(g, k.st));
+      ir_check_kernel<<<ceil_div(k.n_upper, 256), 256, 0, k.st>>>(cbk, k.act, n_tiles, dot_ld, tol * tol, outer, inner);
+      cg_compact_kernel<<<1, 1024, 0, k.st>>>(k.act_buf[k.cur], k.act_buf[k.cur ^ 1], k.n_act, cb.done);
+      cg_commit_count_kernel<<<1, 1, 0, k.st>>>(k.n_act);
+      VGM_LAUNCH_OK();
+      k.cur ^= 1;
+      k.act = k.act_buf[k.cur];
+      VGM_CUDA_OK(cudaMemcpyAsync((void*)k.host_cnt, k.n_act, sizeof(int), cudaMemcpyDeviceToHost, k.st));
+      VGM_CUDA_OK(cudaEventRecord(k.ev, k.st));
+      cnt.gemm += 1; cnt.launches += 4;
+    }
+    // --- corrections: enqueue each chunk's inner solve as soon as its count is known ---
+    bool any = false;
+    for (int c = 0; c < n_chunks; ++c) {
+      IrChunk& k = ch[c];
+      if (k.finished) continue;
+      VGM_CUDA_OK(cudaEventSynchronize(k.ev));
+      k.n_upper = *k.host_cnt;
+      if (g_debug) fprintf(stderr, "[vgm] refinement %d chunk %d: %d of %d systems above tol\n", outer, c, k.n_upper, k.n_rows);
+      if (k.n_upper == 0 || outer == max_outer) { k.finished = true; continue; }
+      any = true;
+      const int n = k.n_upper;
+      VGM_TRY(ir_inner_init(k.ir, cb.R, Lambda, cb.rr, k.act, n, T, ld, ops->G_shift, ops->precond_c, k.st));
+      TcGemmArgs tg;
+      memset(&tg, 0, sizeof(tg));
+      tg.n_rows = n; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = k.ir.acc32; tg.ldo = ld;
+      TcGemmArgs tp = tg;                                   // z' = (s o r) G^T
+      tp.A0 = k.ir.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
+      TcGemmArgs to = tg;                                   // q' = p M^T (bf16 split)
+      to.A0 = k.ir.p_hi; to.A1 = k.ir.p_lo; to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
+      VGM_TRY(tc_gemm(tp, k.st));
+      VGM_TRY(ir_dir(k.ir, n, T, ld, 1, k.st));
+      cnt.launches += 3; cnt.gemm += 1;
+      for (int it = 0; it < inner; ++it) {
+        const int last = (it == inner - 1) ? 1 : 0;
+        VGM_TRY(tc_gemm(to, k.st));
+        VGM_TRY(ir_update(k.ir, n, T, ld, last, k.st));
+        cnt.launches += 2; cnt.gemm += 1;
+        if (last) break;
+        VGM_TRY(tc_gemm(tp, k.st));
+        VGM_TRY(ir_dir(k.ir, n, T, ld, 0, k.st));
+        cnt.launches += 2; cnt.gemm += 1;
+      }
+      VGM_TRY(ir_finish(k.ir, cb.P, X, slot_state, k.act, n, T, ld, k.st));
+      cnt.launches += 1;
+    }
+    if (!any) break;
+  }
+  if (n_chunks > 1) {
+    VGM_CUDA_OK(cudaEventRecord(as.join, as.side));
+    VGM_CUDA_OK(cudaStreamWaitEvent(s, as.join, 0));
   }
   return report_convergence(cb, w, rows, n_rows, tol, max_outer * inner, info, cnt, s);
 }

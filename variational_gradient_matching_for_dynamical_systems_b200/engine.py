@@ -51,7 +51,7 @@ class Operators:
         self.G_bf16 = None
         self.M_bf16x2 = None
         self.G_shift = None
-        self.band_M = self.band_G = 0
+        self.band_M = self.band_M_lp = self.band_G = 0
         self.band_D = self.band_of(self.D)
 
     # |B[i][j]| <= 2^-64 max|B| beyond the band: dropping it perturbs any product by less than half an
@@ -90,6 +90,7 @@ class Operators:
         _lib.check(lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
         self.M, self.M_c = M, c
         self.band_M = self.band_of(M)
+        self.band_M_lp = self.band_of(M, rel=2.0 ** -20)
         self.G = None
         return M
 
@@ -111,7 +112,7 @@ class Operators:
         # bf16 (hi, lo) split of M
         self.G_bf16 = torch.zeros((T, ld), dtype=torch.bfloat16, device=self.dev)
         _lib.check(lib.vgm_convert_bf16(G.data_ptr(), self.G_bf16.data_ptr(), T, ld, _lib.stream_ptr()))
-        self.band_G = self.band_of(G, rel=2.0 ** -9)
+        self.band_G = self.band_of(G, rel=2.0 ** -6)
         self.M_bf16x2 = torch.zeros((2, T, ld), dtype=torch.bfloat16, device=self.dev)
         _lib.check(lib.vgm_split_bf16(self.M.data_ptr(), self.M_bf16x2.data_ptr(), T, ld, _lib.stream_ptr()))
         return G
@@ -309,6 +310,7 @@ class VGMEngine:
         self._cops.G_shift = self.ops.G_shift
         self._cops.precond_c = self.SCALE_FRAC * self.ops.G_shift / self.SHIFT_FRAC if mixed else 0.0
         self._cops.band_G = self.ops.band_G
+        self._cops.band_M_lp = self.ops.band_M_lp
 
     def _set_theta_star(self, theta_star=None):
         if theta_star is not None:
