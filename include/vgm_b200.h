@@ -275,6 +275,10 @@ typedef struct {
   const int* ode_state;
   int theta_mode; /* 0: plug theta_literal into R,r (reference, proxies...py:211); 1: plug the fresh theta */
   double theta_literal[8];
+  /* vgm_iteration_host only: when out_n_rows > 0 the updated states are the rows out_row0 + i * out_row_stride
+   * (i < out_n_rows) and only those are copied back to the host (one strided copy); the rows of states that the
+   * sweep does not touch (observed + clamped, proxies...py:175-179) are then left as they are in X_host_out. */
+  int out_row0, out_row_stride, out_n_rows;
 } vgm_model_tables;
 size_t vgm_iteration_ws_bytes(const vgm_model_tables* model, const vgm_sweep_plan* plan);
 int vgm_iteration_device(const vgm_program* prog, const vgm_model_tables* model, const vgm_sweep_plan* plan,

@@ -316,6 +316,20 @@ def test_lorenz96_plain_cg_matches_too(pkg):
     assert relerr(eng.get_states(), g["states"][0]) < TOL
 
 
+@pytest.mark.parametrize("rows_only", [False, True])
+def test_host_buffer_iteration_matches_reference_golden(pkg, rows_only):
+    """vgm_iteration_host: pinned host buffers in, host buffers out (the end-to-end path bench.py times)."""
+    g = load("lorenz96_K12_T100.npz")
+    eng = _engine_from_golden(pkg, g, vo.lorenz96_ode_lines(12), ["_alpha"])
+    Xh = torch.zeros((eng.K, eng.ld), dtype=torch.float64).pin_memory()
+    Xh[:, :eng.T] = torch.from_numpy(np.ascontiguousarray(g["X0"].T))
+    out = Xh.clone().pin_memory()
+    th = torch.zeros(1, dtype=torch.float64).pin_memory()
+    eng.iteration_host(Xh, th, out, updated_rows_only=rows_only)
+    assert relerr(th.numpy(), g["thetas"][0]) < TOL
+    assert relerr(out[:, :eng.T].numpy().T, g["states"][0]) < TOL
+
+
 @pytest.mark.parametrize("fname", ["lotka_volterra_T50.npz", "lorenz_attractor_T150.npz",
                                    "protein_transduction_T99.npz"])
 def test_multi_parameter_models_vs_patched_reference_golden(pkg, fname):

@@ -152,7 +152,16 @@ extern "C" int vgm_iteration_host(const vgm_program* prog, const vgm_model_table
   int rc = vgm_iteration_device(prog, model, plan, ops, opts, X_dev, DX_dev, theta_dev, stats_dev, ws, ws_bytes, info,
                                 stream);
   if (rc != VGM_OK && rc != VGM_ENOTCONV) return rc;
-  VGM_CUDA_OK(cudaMemcpyAsync(X_host_out, X_dev, bytes, cudaMemcpyDeviceToHost, s));
+  if (model->out_n_rows > 0 && model->out_row_stride > 0 &&
+      model->out_row0 + (size_t)(model->out_n_rows - 1) * model->out_row_stride < (size_t)model->n_states) {
+    // only the rows the sweep updated: one strided (2-D) copy
+    const size_t row_bytes = (size_t)plan->ld * sizeof(double), pitch = row_bytes * model->out_row_stride;
+    const size_t off = (size_t)model->out_row0 * plan->ld;
+    VGM_CUDA_OK(cudaMemcpy2DAsync(X_host_out + off, pitch, X_dev + off, pitch, row_bytes, model->out_n_rows,
+                                  cudaMemcpyDeviceToHost, s));
+  } else {
+    VGM_CUDA_OK(cudaMemcpyAsync(X_host_out, X_dev, bytes, cudaMemcpyDeviceToHost, s));
+  }
   VGM_CUDA_OK(cudaMemcpyAsync(theta_host, theta_dev, model->n_param * sizeof(double), cudaMemcpyDeviceToHost, s));
   VGM_CUDA_OK(cudaStreamSynchronize(s));
   return rc;

@@ -436,21 +436,24 @@ struct IrChunk {
   bool finished = false;
 };
 
+constexpr int IR_MAX_CHUNKS = 4;
 struct IrAsync {                   // created once, kept for the life of the process
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev[2] = {nullptr, nullptr}, fork = nullptr, join = nullptr;
-  int* host_cnt = nullptr;         // pinned, 2 x 16 ints
+  cudaStream_t side[IR_MAX_CHUNKS] = {};       // side[0] unused: chunk 0 runs on the caller's stream
+  cudaEvent_t ev[IR_MAX_CHUNKS] = {}, join[IR_MAX_CHUNKS] = {}, fork = nullptr;
+  int* host_cnt = nullptr;         // pinned, IR_MAX_CHUNKS x 16 ints
 };
 static IrAsync g_ir_async;
 
 static int ir_async_init() {
   IrAsync& a = g_ir_async;
-  if (a.side) return VGM_OK;
-  VGM_CUDA_OK(cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) VGM_CUDA_OK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
+  if (a.host_cnt) return VGM_OK;
+  for (int i = 0; i < IR_MAX_CHUNKS; ++i) {
+    if (i > 0) VGM_CUDA_OK(cudaStreamCreateWithFlags(&a.side[i], cudaStreamNonBlocking));
+    VGM_CUDA_OK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
+    VGM_CUDA_OK(cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming));
+  }
   VGM_CUDA_OK(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
-  VGM_CUDA_OK(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
-  VGM_CUDA_OK(cudaHostAlloc((void**)&a.host_cnt, 32 * sizeof(int), cudaHostAllocDefault));
+  VGM_CUDA_OK(cudaHostAlloc((void**)&a.host_cnt, IR_MAX_CHUNKS * 16 * sizeof(int), cudaHostAllocDefault));
   return VGM_OK;
 }
 
@@ -463,7 +466,16 @@ static IrBuf ir_view(const IrBuf& b, int row0, int ld) {
   return v;
 }
 
-constexpr int IR_CHUNK_MIN_ROWS = 4096;   // below this a level runs as one chunk on the caller's stream
+constexpr int IR_CHUNK_MIN_ROWS = 4096;   // a chunk is at least this many rows; smaller levels run as one chunk
+static int ir_chunk_target() {
+  static int n = 0;
+  if (!n) {
+    const char* e = getenv("VGM_IR_CHUNKS");
+    n = e ? atoi(e) : 2;
+    n = max(1, min(IR_MAX_CHUNKS, n));
+  }
+  return n;
+}
 
 static int ir_solve(const vgm_operators* ops, const double* Lambda, const double* rhs, double* X,
                     const int* slot_state, const int* slot_has_self, const int* rows, int n_rows, int T, int ld,
@@ -479,19 +491,19 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
   IrAsync& as = g_ir_async;
   const int dot_ld = ceil_div(T, 64);                    // row stride of pq_part (its allocation bound)
 
-  const int n_chunks = (n_rows >= 2 * IR_CHUNK_MIN_ROWS) ? 2 : 1;
-  IrChunk ch[2];
+  const int n_chunks = max(1, min(ir_chunk_target(), n_rows / IR_CHUNK_MIN_ROWS));
+  IrChunk ch[IR_MAX_CHUNKS];
+  // chunk boundaries on multiples of 128 rows (whole GEMM row tiles)
+  const int per = ((ceil_div(n_rows, n_chunks) + 127) / 128) * 128;
   for (int c = 0; c < n_chunks; ++c) {
     IrChunk& k = ch[c];
-    // chunk boundaries on multiples of 128 rows (whole GEMM row tiles)
-    const int half = ((n_rows / 2 + 127) / 128) * 128;
-    k.row0 = (c == 0) ? 0 : half;
-    k.n_rows = (n_chunks == 1) ? n_rows : (c == 0 ? half : n_rows - half);
+    k.row0 = min(c * per, n_rows);
+    k.n_rows = min(per, n_rows - k.row0);
     k.act_buf[0] = cb.act[0] + k.row0;
     k.act_buf[1] = cb.act[1] + k.row0;
     k.n_act = cb.n_act + 4 * c;
     k.ir = ir_view(w.ir, k.row0, ld);
-    k.st = (c == 0) ? s : as.side;
+    k.st = (c == 0) ? s : as.side[c];
     k.ev = as.ev[c];
     k.host_cnt = as.host_cnt + 16 * c;
     k.n_upper = k.n_rows;
@@ -499,10 +511,11 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
   }
   if (n_chunks > 1) {
     VGM_CUDA_OK(cudaEventRecord(as.fork, s));
-    VGM_CUDA_OK(cudaStreamWaitEvent(as.side, as.fork, 0));
+    for (int c = 1; c < n_chunks; ++c) VGM_CUDA_OK(cudaStreamWaitEvent(as.side[c], as.fork, 0));
   }
   for (int c = 0; c < n_chunks; ++c) {
     IrChunk& k = ch[c];
+    if (k.n_rows <= 0) { k.finished = true; continue; }
     CgBuf cbk = cb;
     cbk.n_act = k.n_act;
     VGM_CUDA_OK(cudaMemcpyAsync(k.act_buf[0], rows + k.row0, (size_t)k.n_rows * sizeof(int), cudaMemcpyDeviceToDevice, k.st));
@@ -582,9 +595,9 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
     }
     if (!any) break;
   }
-  if (n_chunks > 1) {
-    VGM_CUDA_OK(cudaEventRecord(as.join, as.side));
-    VGM_CUDA_OK(cudaStreamWaitEvent(s, as.join, 0));
+  for (int c = 1; c < n_chunks; ++c) {
+    VGM_CUDA_OK(cudaEventRecord(as.join[c], as.side[c]));
+    VGM_CUDA_OK(cudaStreamWaitEvent(s, as.join[c], 0));
   }
   return report_convergence(cb, w, rows, n_rows, tol, max_outer * inner, info, cnt, s);
 }

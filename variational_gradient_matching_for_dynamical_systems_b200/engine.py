@@ -398,12 +398,20 @@ class VGMEngine:
         return self.last_info
 
     def iteration_host(self, X_host_KT: torch.Tensor, theta_host: torch.Tensor, X_host_out: torch.Tensor = None,
-                       allow_unconverged=False):
+                       allow_unconverged=False, updated_rows_only=False):
         """End-to-end iteration with HOST buffers (vgm_iteration_host): ``X_host_KT`` is a
         (pinned) CPU tensor [K, ld]; the updated proxies go to ``X_host_out`` (default: in
-        place); ``theta_host`` a CPU tensor [p]."""
+        place); ``theta_host`` a CPU tensor [p].  ``updated_rows_only``: copy back only the rows of the
+        hidden states (the others are not changed by the sweep and are left as they are in ``X_host_out``);
+        needs the hidden states to be equally spaced rows, otherwise everything is copied."""
         if X_host_out is None:
             X_host_out = X_host_KT
+        self._mt.out_n_rows = 0
+        h = self.plan.hidden
+        if updated_rows_only and len(h) > 1:
+            step = int(h[1] - h[0])
+            if step > 0 and np.all(np.diff(np.sort(h)) == step):
+                self._mt.out_row0, self._mt.out_row_stride, self._mt.out_n_rows = int(h.min()), step, len(h)
         if self._cops.G is None and self.precondition and self.plan.c.ruu_const and self.plan.n_hidden:
             self.X.copy_(X_host_KT, non_blocking=True)
             self.compute_DX()
