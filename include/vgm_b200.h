@@ -208,6 +208,9 @@ typedef struct {
   int max_iter;      /* FP64 PCG: iteration cap (default 4 T); mixed precision: cap on outer corrections (default 30) */
   int check_every;   /* FP64 PCG: host polls the device-side active count every this many iterations         */
   int inner_iters;   /* mixed precision: FP32 PCG steps per correction (default 10)                           */
+  int optimistic_passes; /* mixed precision: corrections enqueued before the first convergence poll (default 4;
+                            < 0: poll after every pass).  Kernels read the active count on the device, so passes
+                            over converged rows are free; fewer polls keep the queue full on small problems  */
 } vgm_solver_opts;
 
 typedef struct {

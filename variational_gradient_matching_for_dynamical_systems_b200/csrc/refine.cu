@@ -40,6 +40,7 @@ void ir_carve(char*& p, int n, int ld, IrBuf& b) {
 
 // ---- 4-element vector helpers (rows are 16-byte aligned: ld % 8 == 0) --------------------------------
 struct bf4 { __nv_bfloat162 a, b; };
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld_bf4(const __nv_bfloat16* p) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
   const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
@@ -56,7 +57,7 @@ __device__ __forceinline__ void st_bf4(__nv_bfloat16* p, float4 v) {
 __device__ __forceinline__ float bf_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 // The GEMM writes columns < T only: whatever sits in the row padding of acc32 must not reach a dot product.
 __device__ __forceinline__ float4 ld_acc4(const float* p, int i, int T) {
-  float4 v = *reinterpret_cast<const float4*>(p);
+  float4 v = ld_f4(p);
   if (i + 4 > T) {
     if (i + 1 >= T) v.y = 0.f;
     if (i + 2 >= T) v.z = 0.f;
@@ -71,9 +72,10 @@ __device__ __forceinline__ float4 ld_acc4(const float* p, int i, int T) {
 
 __global__ void __launch_bounds__(IR_THREADS)
 ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __restrict__ Lambda,
-                     const double* __restrict__ rr, const int* __restrict__ act, int T, int ld, double shift,
-                     double c) {
+                     const double* __restrict__ rr, const int* __restrict__ act, const int* __restrict__ n_dev, int T,
+                     int ld, double shift, double c) {
   const int j = blockIdx.x;
+  if (n_dev && j >= *n_dev) return;
   const int slot = act[j];
   const double sig = sqrt(rr[slot]);
   const double inv = sig > 0.0 ? 1.0 / sig : 0.0;
@@ -101,20 +103,27 @@ ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __rest
 // REG: the row fits one pass (T <= 4 * IR_THREADS), so z / (p, q) stay in registers and the kernel needs no
 // dynamic shared memory -- its CTAs then co-reside with the persistent tcgen05 GEMM of the other row chunk.
 template <bool REG>
-__global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, int T, int ld, int first) {
+__global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, const int* __restrict__ n_dev, int T, int ld,
+                                                            int first) {
   extern __shared__ float ir_sm[];       // z of this row (!REG)
   __shared__ double red[40];
   const int j = blockIdx.x;
+  if (n_dev && j >= *n_dev) return;
   const size_t o = (size_t)j * ld;
   double part = 0.0;
   float4 zreg = make_float4(0.f, 0.f, 0.f, 0.f);
   IR_ROW_LOOP(i, T) {
     const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
     const float4 sv = ld_bf4(b.s16 + o + i);
-    const float4 r = *reinterpret_cast<const float4*>(b.r32 + o + i);
+    const float4 r = ld_f4(b.r32 + o + i);
     const float4 z = make_float4(sv.x * acc.x, sv.y * acc.y, sv.z * acc.z, sv.w * acc.w);
     if (REG) zreg = z; else *reinterpret_cast<float4*>(ir_sm + i) = z;
     part += (double)r.x * z.x + (double)r.y * z.y + (double)r.z * z.z + (double)r.w * z.w;
+  }
+  float4 hreg = zreg, lreg = zreg;
+  if (REG && !first) {
+    const int i = 4 * threadIdx.x;
+    if (i < T) { hreg = ld_bf4(b.p_hi + o + i); lreg = ld_bf4(b.p_lo + o + i); }
   }
   const double rz_new = block_sum(part, red);
   const double rz_old = first ? 0.0 : b.rz[j];
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, int T, int 
   IR_ROW_LOOP(i, T) {
     float4 p = REG ? zreg : *reinterpret_cast<const float4*>(ir_sm + i);
     if (!first) {
-      const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
+      const float4 h = REG ? hreg : ld_bf4(b.p_hi + o + i), l = REG ? lreg : ld_bf4(b.p_lo + o + i);
       p.x += beta * (h.x + l.x); p.y += beta * (h.y + l.y); p.z += beta * (h.z + l.z); p.w += beta * (h.w + l.w);
     }
     const float4 hi = make_float4(bf_round(p.x), bf_round(p.y), bf_round(p.z), bf_round(p.w));
@@ -133,19 +142,21 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, int T, int 
 }
 
 template <bool REG>
-__global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, int T, int ld, int last) {
+__global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const int* __restrict__ n_dev, int T, int ld,
+                                                               int last) {
   extern __shared__ float ir_sm[];       // p and q of this row (!REG)
   __shared__ double red[40];
   float* sp = ir_sm;
   float* sq = ir_sm + ((T + 3) & ~3);
   const int j = blockIdx.x;
+  if (n_dev && j >= *n_dev) return;
   const size_t o = (size_t)j * ld;
   double part = 0.0;
   float4 preg = make_float4(0.f, 0.f, 0.f, 0.f), qreg = preg;
   IR_ROW_LOOP(i, T) {
     const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
     const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
-    const float4 lam = *reinterpret_cast<const float4*>(b.lam32 + o + i);
+    const float4 lam = ld_f4(b.lam32 + o + i);
     const float4 p = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
     const float4 q = make_float4(fmaf(lam.x, p.x, acc.x), fmaf(lam.y, p.y, acc.y), fmaf(lam.z, p.z, acc.z),
                                  fmaf(lam.w, p.w, acc.w));
@@ -155,19 +166,28 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, int T, i
     }
     part += (double)p.x * q.x + (double)p.y * q.y + (double)p.z * q.z + (double)p.w * q.w;
   }
+  // REG: issue the loads of the second phase before the row-wide reduction so their latency hides behind it
+  float4 dreg = preg, rreg = preg, sreg = preg;
+  if (REG) {
+    const int i = 4 * threadIdx.x;
+    if (i < T) {
+      dreg = ld_f4(b.d32 + o + i);
+      if (!last) { rreg = ld_f4(b.r32 + o + i); sreg = ld_bf4(b.s16 + o + i); }
+    }
+  }
   const double pq = block_sum(part, red);
   const float alpha = (pq > 0.0) ? (float)(b.rz[j] / pq) : 0.f;
   IR_ROW_LOOP(i, T) {
     const float4 p = REG ? preg : *reinterpret_cast<const float4*>(sp + i);
     const float4 q = REG ? qreg : *reinterpret_cast<const float4*>(sq + i);
-    float4 d = *reinterpret_cast<const float4*>(b.d32 + o + i);
+    float4 d = REG ? dreg : ld_f4(b.d32 + o + i);
     d.x = fmaf(alpha, p.x, d.x); d.y = fmaf(alpha, p.y, d.y); d.z = fmaf(alpha, p.z, d.z); d.w = fmaf(alpha, p.w, d.w);
     *reinterpret_cast<float4*>(b.d32 + o + i) = d;
     if (!last) {
-      float4 r = *reinterpret_cast<const float4*>(b.r32 + o + i);
+      float4 r = REG ? rreg : ld_f4(b.r32 + o + i);
       r.x = fmaf(-alpha, q.x, r.x); r.y = fmaf(-alpha, q.y, r.y); r.z = fmaf(-alpha, q.z, r.z); r.w = fmaf(-alpha, q.w, r.w);
       *reinterpret_cast<float4*>(b.r32 + o + i) = r;
-      const float4 sv = ld_bf4(b.s16 + o + i);
+      const float4 sv = REG ? sreg : ld_bf4(b.s16 + o + i);
       st_bf4(b.rsb + o + i, make_float4(sv.x * r.x, sv.y * r.y, sv.z * r.z, sv.w * r.w));
     }
   }
@@ -175,8 +195,9 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, int T, i
 
 __global__ void __launch_bounds__(IR_THREADS)
 ir_finish_kernel(IrBuf b, double* __restrict__ P, double* __restrict__ X, const int* __restrict__ slot_state,
-                 const int* __restrict__ act, int T, int ld) {
+                 const int* __restrict__ act, const int* __restrict__ n_dev, int T, int ld) {
   const int j = blockIdx.x;
+  if (n_dev && j >= *n_dev) return;
   const int slot = act[j];
   const double sig = b.sigma[j];
   const float* d = b.d32 + (size_t)j * ld;
@@ -190,39 +211,39 @@ ir_finish_kernel(IrBuf b, double* __restrict__ P, double* __restrict__ X, const 
 }
 
 int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
-                  int T, int ld, double shift, double c, cudaStream_t s) {
+                  const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * (16.0 + 16.0), s);
-  ir_inner_init_kernel<<<n, IR_THREADS, 0, s>>>(b, R, Lambda, rr, act, T, ld, shift, c);
+  ir_inner_init_kernel<<<n, IR_THREADS, 0, s>>>(b, R, Lambda, rr, act, n_dev, T, ld, shift, c);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }
 
-int ir_dir(const IrBuf& b, int n, int T, int ld, int first, cudaStream_t s) {
+int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   // reads acc32 4, s16 2, r32 4, (p_hi, p_lo 4); writes p_hi, p_lo 4
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * (first ? 14.0 : 18.0), s);
-  if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, T, ld, first);
-  else ir_dir_kernel<false><<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, first);
+  if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, first);
+  else ir_dir_kernel<false><<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, first);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }
 
-int ir_update(const IrBuf& b, int n, int T, int ld, int last, cudaStream_t s) {
+int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4, s16 2); writes d32 4, (r32 4, rsb 2)
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * (last ? 20.0 : 32.0), s);
-  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, T, ld, last);
-  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, T, ld, last);
+  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, last);
+  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, last);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }
 
-int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, int T, int ld,
-              cudaStream_t s) {
+int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, const int* n_dev,
+              int T, int ld, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * 28.0, s);
-  ir_finish_kernel<<<n, IR_THREADS, 0, s>>>(b, P, X, slot_state, act, T, ld);
+  ir_finish_kernel<<<n, IR_THREADS, 0, s>>>(b, P, X, slot_state, act, n_dev, T, ld);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }

@@ -17,14 +17,15 @@ size_t ir_ws_bytes(int n, int ld);
 void ir_carve(char*& p, int n, int ld, IrBuf& b);
 
 // r32 = R[slot]/sigma, lam32 = Lambda[slot], s = sqrt((shift + c)/(Lambda + c)) (1 if c <= 0), rsb = bf16(s r), d = 0
+// `n` is a host upper bound of the row count; `n_dev` (optional) the exact device-side count.
 int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
-                  int T, int ld, double shift, double c, cudaStream_t s);
+                  const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s);
 // z = s o acc32; rz' = r.z; beta = first ? 0 : rz'/rz; p = z + beta p  ->  (p_hi, p_lo)
-int ir_dir(const IrBuf& b, int n, int T, int ld, int first, cudaStream_t s);
+int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s);
 // q = acc32 + lam o p; alpha = rz / p.q; d += alpha p; r -= alpha q; rsb = bf16(s o r)
-int ir_update(const IrBuf& b, int n, int T, int ld, int last, cudaStream_t s);
+int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, cudaStream_t s);
 // x = P[slot] + sigma d; P[slot] = x; X[state(slot)] = x
-int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, int T, int ld,
-              cudaStream_t s);
+int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, const int* n_dev,
+              int T, int ld, cudaStream_t s);
 
 }  // namespace vgm

@@ -421,8 +421,9 @@ __global__ void ir_check_kernel(CgBuf cb, const int* __restrict__ act, int n_til
 //                         tcgen05 GEMM (3 products, ~2^-16) and the preconditioner S G S (G = (M + shift I)^-1
 //                         in bf16, S the diagonal scaling of vgm_operators.precond_c).
 // Each correction contracts the error by ~1e-3..1e-4, so 4-5 FP64 GEMMs replace the ~60 of FP64 PCG.
-// Large levels are split into two independent row chunks driven on two streams: the tensor-core GEMMs of
-// one chunk are bound by L2->SMEM traffic, the vector kernels of the other by HBM, so they overlap.
+// A level can be split into independent row chunks driven on separate streams (VGM_IR_CHUNKS, default 1): that
+// overlapped the L2-bound tensor-core GEMMs of one chunk with the HBM-bound vector kernels of another while
+// the GEMM epilogue was inefficient; with the TMA-store epilogue every kernel is HBM-bound and one chunk wins.
 struct IrChunk {
   int row0 = 0, n_rows = 0;        // slice of the level's row list
   int cur = 0, n_upper = 0;
@@ -471,7 +472,7 @@ static int ir_chunk_target() {
   static int n = 0;
   if (!n) {
     const char* e = getenv("VGM_IR_CHUNKS");
-    n = e ? atoi(e) : 2;
+    n = e ? atoi(e) : 1;
     n = max(1, min(IR_MAX_CHUNKS, n));
   }
   return n;
@@ -483,6 +484,9 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
   const double tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
   const int max_outer = (opts && opts->max_iter > 0) ? opts->max_iter : 30;
   const int inner = (opts && opts->inner_iters > 0) ? opts->inner_iters : 10;
+  // corrections enqueued back to back before the host looks at a convergence count for the first time: the
+  // kernels read the exact active count on the device, so a pass over already converged rows costs nothing
+  const int optimistic = (opts && opts->optimistic_passes > 0) ? opts->optimistic_passes : (opts && opts->optimistic_passes < 0 ? 0 : 4);
   CgBuf& cb = w.cb;
   const int th = row_threads(T);
   const __nv_bfloat16* M_hi = (const __nv_bfloat16*)ops->M_bf16x2;
@@ -563,34 +567,36 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
     for (int c = 0; c < n_chunks; ++c) {
       IrChunk& k = ch[c];
       if (k.finished) continue;
-      VGM_CUDA_OK(cudaEventSynchronize(k.ev));
-      k.n_upper = *k.host_cnt;
-      if (g_debug) fprintf(stderr, "[vgm] refinement %d chunk %d: %d of %d systems above tol\n", outer, c, k.n_upper, k.n_rows);
-      if (k.n_upper == 0 || outer == max_outer) { k.finished = true; continue; }
+      if (outer >= optimistic || outer == max_outer) {
+        VGM_CUDA_OK(cudaEventSynchronize(k.ev));
+        k.n_upper = *k.host_cnt;
+        if (g_debug) fprintf(stderr, "[vgm] refinement %d chunk %d: %d of %d systems above tol\n", outer, c, k.n_upper, k.n_rows);
+        if (k.n_upper == 0 || outer == max_outer) { k.finished = true; continue; }
+      }
       any = true;
-      const int n = k.n_upper;
-      VGM_TRY(ir_inner_init(k.ir, cb.R, Lambda, cb.rr, k.act, n, T, ld, ops->G_shift, ops->precond_c, k.st));
+      const int n = k.n_upper;                              // host upper bound; k.n_act is exact
+      VGM_TRY(ir_inner_init(k.ir, cb.R, Lambda, cb.rr, k.act, n, k.n_act, T, ld, ops->G_shift, ops->precond_c, k.st));
       TcGemmArgs tg;
       memset(&tg, 0, sizeof(tg));
-      tg.n_rows = n; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = k.ir.acc32; tg.ldo = ld;
+      tg.n_rows = n; tg.n_rows_dev = k.n_act; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = k.ir.acc32; tg.ldo = ld;
       TcGemmArgs tp = tg;                                   // z' = (s o r) G^T
       tp.A0 = k.ir.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
       TcGemmArgs to = tg;                                   // q' = p M^T (bf16 split)
       to.A0 = k.ir.p_hi; to.A1 = k.ir.p_lo; to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
       VGM_TRY(tc_gemm(tp, k.st));
-      VGM_TRY(ir_dir(k.ir, n, T, ld, 1, k.st));
+      VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 1, k.st));
       cnt.launches += 3; cnt.gemm += 1;
       for (int it = 0; it < inner; ++it) {
         const int last = (it == inner - 1) ? 1 : 0;
         VGM_TRY(tc_gemm(to, k.st));
-        VGM_TRY(ir_update(k.ir, n, T, ld, last, k.st));
+        VGM_TRY(ir_update(k.ir, n, k.n_act, T, ld, last, k.st));
         cnt.launches += 2; cnt.gemm += 1;
         if (last) break;
         VGM_TRY(tc_gemm(tp, k.st));
-        VGM_TRY(ir_dir(k.ir, n, T, ld, 0, k.st));
+        VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 0, k.st));
         cnt.launches += 2; cnt.gemm += 1;
       }
-      VGM_TRY(ir_finish(k.ir, cb.P, X, slot_state, k.act, n, T, ld, k.st));
+      VGM_TRY(ir_finish(k.ir, cb.P, X, slot_state, k.act, n, k.n_act, T, ld, k.st));
       cnt.launches += 1;
     }
     if (!any) break;

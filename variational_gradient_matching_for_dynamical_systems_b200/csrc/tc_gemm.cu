@@ -12,11 +12,12 @@
 //   warp 0     TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier ring; one stage = the A and B
 //                               k-blocks of every split part, loaded once and used by all three products)
 //   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=128, K=16; FP32 in TMEM)
-//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> registers -> 128-byte row segments -> global)
+//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> registers -> swizzled smem chunk -> TMA store, 2-deep ring)
 // Two 128-column TMEM accumulators are double-buffered so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Out-of-range rows / columns / K are zero-filled by TMA.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "vgm_common.cuh"
 #include "vgm_profile.cuh"
@@ -29,12 +30,14 @@ constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_TILE_BYTES = 128 * TC_BK * 2;                 // one 128 x 64 bf16 operand tile (A or B part)
 constexpr int TC_TMEM_COLS = 2 * TC_BN;
+constexpr int TC_OUT_TILE_BYTES = 32 * 32 * 4;                 // one 32-row x 32-column FP32 chunk of the output
+constexpr int TC_OUT_STAGING = TC_EPI_WARPS * 2 * TC_OUT_TILE_BYTES;   // two chunks per epilogue warp (TMA store ring)
 template <bool SPLIT>
 struct TcCfg {
   static constexpr int PARTS = SPLIT ? 2 : 1;                  // (hi, lo) or hi only, for A and for B
   static constexpr int STAGE_BYTES = 2 * PARTS * TC_TILE_BYTES;
   static constexpr int STAGES = SPLIT ? 3 : 6;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + TC_OUT_STAGING + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -66,6 +69,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -111,7 +120,7 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
                               ((uint32_t)(TC_BM >> 4) << 24);
 
 struct TcMaps {
-  CUtensorMap a0, a1, b0, b1;
+  CUtensorMap a0, a1, b0, b1, out;
 };
 
 // k-block range of column tile ct
@@ -134,7 +143,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
   // 1024-byte alignment is required by the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   // stage layout: [A0][A1 if split][B0][B1 if split], 16 KB each
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  unsigned char* out_stage = smem + STAGES * Cfg::STAGE_BYTES;   // [EPI_WARPS][2][32 x 128 B], 128B-swizzled rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + TC_OUT_STAGING);
   uint64_t* full_bar = bars;                                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;                        // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;                    // [2]
@@ -142,7 +152,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_rows = a.n_rows;
+  const int n_rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int row_tiles = (n_rows + TC_BM - 1) / TC_BM;
   const int col_tiles = (a.M + TC_BN - 1) / TC_BN;
   const int n_tiles = row_tiles * col_tiles;
@@ -236,36 +246,43 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
     int it = 0;
+    int epi_buf = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int rt = tile / col_tiles, ct = tile % col_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int j = rt * TC_BM + q * 32 + lane;           // this thread's TMEM lane = compact row j
-      const bool row_ok = j < n_rows;
-      float* __restrict__ orow = a.out + (size_t)(row_ok ? j : 0) * a.ldo;
+      // This thread's TMEM lane is row rt*128 + q*32 + lane.  A warp moves its 32 x 32 chunk through shared
+      // memory (the 128B swizzle TMA expects: 16-byte piece i of row r sits at piece i ^ (r & 7), which also
+      // makes the row-per-thread writes bank-conflict free) and one lane hands it to a TMA store, so global
+      // memory sees whole 128-byte lines; rows >= n_rows and columns >= M are clipped by the tensor map.
       const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16);
+      unsigned char* my_stage = out_stage + (warp - 2) * 2 * TC_OUT_TILE_BYTES;
 #pragma unroll 1
       for (int c = 0; c < TC_BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);                          // warp-collective: executed by all lanes
         const int m0 = ct * TC_BN + c;
-        if (!row_ok || m0 >= a.M) continue;
-        if (m0 + 32 <= a.M) {
+        if (m0 >= a.M) continue;                          // uniform
+        // the store that used this buffer two chunks ago must have read it (one newer store may be pending)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        unsigned char* sb = my_stage + epi_buf * TC_OUT_TILE_BYTES;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<uint4*>(orow + m0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (m0 + i < a.M) orow[m0 + i] = __uint_as_float(v[i]);
-        }
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(sb + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && !(a.debug & 1)) tma_store_2d(&maps.out, sb, m0, rt * TC_BM + q * 32);
+        epi_buf ^= 1;
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
   }
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // output stores done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -281,7 +298,8 @@ typedef CUresult (*cuTensorMapEncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, 
                                              CUtensorMapFloatOOBfill);
 static cuTensorMapEncodeTiled_t g_encode = nullptr;
 
-static int make_bf16_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+static int make_map(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rows, int cols,
+                    int ld, int box_cols, int box_rows) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -293,10 +311,10 @@ static int make_bf16_map(CUtensorMap* map, const void* base, int rows, int cols,
     g_encode = (cuTensorMapEncodeTiled_t)fn;
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = g_encode(map, dtype, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -304,6 +322,9 @@ static int make_bf16_map(CUtensorMap* map, const void* base, int rows, int cols,
     return VGM_EDRIVER;
   }
   return VGM_OK;
+}
+static int make_bf16_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+  return make_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, TC_BK, box_rows);
 }
 
 template <bool SPLIT>
@@ -336,6 +357,9 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
     VGM_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   const bool split = args.A1 != nullptr;
+  static const int dbg = getenv("VGM_TC_DEBUG") ? atoi(getenv("VGM_TC_DEBUG")) : 0;
+  TcGemmArgs largs = args;
+  largs.debug = dbg;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   VGM_TRY(make_bf16_map(&maps.a0, args.A0, args.n_rows, args.K, args.lda, TC_BM));
@@ -344,6 +368,7 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
     VGM_TRY(make_bf16_map(&maps.a1, args.A1, args.n_rows, args.K, args.lda, TC_BM));
     VGM_TRY(make_bf16_map(&maps.b1, args.B1, args.M, args.K, args.ldb, TC_BN));
   }
+  VGM_TRY(make_map(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, args.out, args.n_rows, args.M, args.ldo, 32, 32));
   // executed MMA flops (band) and compulsory HBM bytes (A parts once, FP32 output once)
   double ksum = 0.0;
   for (int m0 = 0; m0 < args.M; m0 += TC_BN)
@@ -351,7 +376,7 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
   const double flops = 2.0 * args.n_rows * TC_BN * ksum * (split ? 3.0 : 1.0);
   const double bytes = (double)args.n_rows * args.K * 2.0 * (split ? 2.0 : 1.0) + (double)args.n_rows * args.M * 4.0;
   ProfScope prof(PROF_TCGEMM, flops, bytes, s);
-  return split ? tc_launch<true>(maps, args, n_sm, s) : tc_launch<false>(maps, args, n_sm, s);
+  return split ? tc_launch<true>(maps, largs, n_sm, s) : tc_launch<false>(maps, largs, n_sm, s);
 }
 
 __global__ void f64_to_bf16_kernel(const double* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {

@@ -7,7 +7,8 @@ namespace vgm {
 
 // out[j][m] = sum_k A0[j][k] B0[m][k]  (+ A1 B0^T + A0 B1^T when split), raw FP32 accumulators.
 struct TcGemmArgs {
-  int n_rows;               // rows of A* and out (compact)
+  int n_rows;               // rows of A* and out (compact); host upper bound when n_rows_dev is set
+  const int* n_rows_dev;    // optional device-side row count (<= n_rows): lets a solver enqueue passes without host polls
   int M, K;                 // output columns, contraction length
   int band;                 // B*[m][k] == 0 for |m - k| > band (<= 0: dense)
   const void* A0;           // [n_rows][lda] bf16
@@ -18,6 +19,7 @@ struct TcGemmArgs {
   int ldb;
   float* out;               // [n_rows][ldo] fp32
   int ldo;
+  int debug;                // timing experiments only (VGM_TC_DEBUG): 1 = skip the epilogue stores
 };
 
 int tc_gemm(const TcGemmArgs& args, cudaStream_t s);
