@@ -211,6 +211,9 @@ typedef struct {
   int optimistic_passes; /* mixed precision: corrections enqueued before the first convergence poll (default 4;
                             < 0: poll after every pass).  Kernels read the active count on the device, so passes
                             over converged rows are free; fewer polls keep the queue full on small problems  */
+  int small_level_solver; /* 1: dependency levels of <= 8 systems are solved by one CTA per system (FP32 banded Cholesky
+                            + FP64 refinement in a single launch, csrc/small_solve.cu) instead of the batched solver.
+                            Off by default: at T=1000 it takes 1.4 ms against 1.1 ms for the ~190 tiny launches  */
 } vgm_solver_opts;
 
 typedef struct {

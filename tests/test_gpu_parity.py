@@ -199,6 +199,27 @@ def test_mixed_precision_solver_matches_fp64_pcg_and_oracle(pkg):
     assert relerr(res["mixed"][0], res["pcg"][0]) < 1e-10
 
 
+def test_all_hidden_chain_with_the_single_cta_solver(pkg):
+    """Lorenz96 K=12, T=160 with EVERY state hidden: 12 dependency levels of one system each (the reference's
+    sequential order); each level is one launch of the banded-Cholesky + refinement kernel (small_solve.cu)."""
+    p, _lib, engine = pkg
+    K, T = 12, 160
+    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=7)
+    rng = np.random.default_rng(8)
+    X0 = Xtrue + 0.3 * rng.standard_normal((T, K))
+    D, A, *_ = vo.kernel_function(t, t, "rbf", [0.0625, 1.0])
+    hidden = list(range(K))
+    Xref = vo.lorenz96_state_sweep(X0, 8.0, D, hidden)
+    eng = engine.VGMEngine(p.OdeModel.lorenz96(K), D, A, hidden=hidden, solver="mixed", small_level_solver=True)
+    assert eng.plan.c.n_levels == K
+    eng.set_states(X0)
+    eng.theta_step()
+    info = eng.state_sweep()
+    assert relerr(eng.get_states(), Xref) < TOL, info
+    assert info["unconverged"] == 0
+    assert info["kernel_launches"] < 8 * K, info      # a handful of launches per level, not ~190
+
+
 def _kernel_function_gpu(_lib, t, t2, ktype, kparam):
     lib = _lib.load()
     T, T2 = len(t), len(t2)

@@ -62,7 +62,7 @@ class Operators(C.Structure):
 
 class SolverOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("check_every", C.c_int), ("inner_iters", C.c_int),
-                ("optimistic_passes", C.c_int)]
+                ("optimistic_passes", C.c_int), ("small_level_solver", C.c_int)]
 
 
 class SweepInfo(C.Structure):

@@ -5,6 +5,7 @@
 #include <cuda.h>
 
 #include "vgm_common.cuh"
+#include "vgm_profile.cuh"
 
 // ---------------------------------------------------------------------------------------
 // Built-in program: Lorenz96, f_k = (x_{k+1} - x_{k-2}) x_{k-1} - x_k + alpha  (Lorenz96_ODEs.txt:1-10)
@@ -80,6 +81,7 @@ int program_param_stats(const vgm_program* prog, const double* X, const double* 
                         cudaStream_t s) {
   const int grid = ceil_div(n_odes, 8);
   const int block = prog_threads(T);
+  ProfScope prof(PROF_ASSEMBLE, 0.0, 16.0 * n_odes * T, s);       // X and D.X once
   if (prog->builtin) {
     lorenz96_prog::vgm_lorenz96_param_stats<<<grid, block, 0, s>>>(X, DX, ld, T, n_odes, ode_class, ode_idx, ode_state,
                                                                    partial);
@@ -97,6 +99,8 @@ int program_state_assemble(const vgm_program* prog, const vgm_sweep_plan* pl, co
   if (pl->n_hidden == 0) return VGM_OK;
   const int grid = pl->n_hidden, block = prog_threads(pl->T);
   int ld = pl->ld, T = pl->T, nh = pl->n_hidden;
+  // writes Lambda, rhs, r_uu (24 B) and reads ~arity+pairs rows of X / D.X through L1/L2 (~8 distinct rows: 64 B)
+  ProfScope prof(PROF_ASSEMBLE, 0.0, 88.0 * nh * T, s);
   if (prog->builtin) {
     lorenz96_prog::vgm_lorenz96_state_assemble<<<grid, block, 0, s>>>(
         X, DX0, ld, T, nh, pl->pair_ptr, pl->pair_ode, pl->pair_code, pl->pair_live, pl->pair_self, pl->ode_idx,

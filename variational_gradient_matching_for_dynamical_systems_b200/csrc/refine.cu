@@ -141,6 +141,82 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, const int* 
   if (threadIdx.x == 0) b.rz[j] = rz_new;
 }
 
+// One WARP per system (T <= 1024, T % 8 == 0): a lane keeps its 4 groups of 8 elements in registers, every load of
+// the row is in flight at once (~14 KB per warp), bf16 arrays move 16 bytes per lane like the FP32 ones, and the row
+// dot product needs warp shuffles only -- no __syncthreads.
+constexpr int IR_WG = 4;
+struct f8 { float4 a, b; };
+__device__ __forceinline__ f8 ld_bf8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
+  const float2 v3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+  f8 r;
+  r.a = make_float4(v0.x, v0.y, v1.x, v1.y);
+  r.b = make_float4(v2.x, v2.y, v3.x, v3.y);
+  return r;
+}
+__device__ __forceinline__ void st_bf8(__nv_bfloat16* p, float4 a, float4 b) {
+  const __nv_bfloat162 q0 = __floats2bfloat162_rn(a.x, a.y), q1 = __floats2bfloat162_rn(a.z, a.w);
+  const __nv_bfloat162 q2 = __floats2bfloat162_rn(b.x, b.y), q3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&q0); u.y = *reinterpret_cast<const uint32_t*>(&q1);
+  u.z = *reinterpret_cast<const uint32_t*>(&q2); u.w = *reinterpret_cast<const uint32_t*>(&q3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 axpy4(float s, float4 a, float4 b) {
+  return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
+}
+__device__ __forceinline__ float4 bfr4(float4 a) { return make_float4(bf_round(a.x), bf_round(a.y), bf_round(a.z), bf_round(a.w)); }
+__device__ __forceinline__ double dot4(float4 a, float4 b) {
+  return (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+}
+
+__global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const int* __restrict__ n_dev, int n, int T,
+                                                                 int ld, int first) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (IR_THREADS / 32) + (threadIdx.x >> 5);
+  const int nn = n_dev ? min(*n_dev, n) : n;
+  if (j >= nn) return;
+  const size_t o = (size_t)j * ld;
+  f8 z[IR_WG], pp[IR_WG];
+  double part = 0.0;
+#pragma unroll
+  for (int g = 0; g < IR_WG; ++g) {
+    const int i = 8 * (lane + 32 * g);
+    z[g].a = z[g].b = pp[g].a = pp[g].b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < T) {                                              // T % 8 == 0: whole groups only
+      const float4 a0 = ld_f4(b.acc32 + o + i), a1 = ld_f4(b.acc32 + o + i + 4);
+      const f8 sv = ld_bf8(b.s16 + o + i);
+      const float4 r0 = ld_f4(b.r32 + o + i), r1 = ld_f4(b.r32 + o + i + 4);
+      if (!first) {
+        const f8 h = ld_bf8(b.p_hi + o + i), l = ld_bf8(b.p_lo + o + i);
+        pp[g].a = add4(h.a, l.a); pp[g].b = add4(h.b, l.b);
+      }
+      z[g].a = mul4(sv.a, a0); z[g].b = mul4(sv.b, a1);
+      part += dot4(r0, z[g].a) + dot4(r1, z[g].b);
+    }
+  }
+  const double rz_new = warp_sum(part);
+  const double rz_old = first ? 0.0 : b.rz[j];
+  const float beta = (first || !(rz_old > 0.0)) ? 0.f : (float)(rz_new / rz_old);
+#pragma unroll
+  for (int g = 0; g < IR_WG; ++g) {
+    const int i = 8 * (lane + 32 * g);
+    if (i < T) {
+      const float4 p0 = axpy4(beta, pp[g].a, z[g].a), p1 = axpy4(beta, pp[g].b, z[g].b);
+      const float4 h0 = bfr4(p0), h1 = bfr4(p1);
+      st_bf8(b.p_hi + o + i, h0, h1);
+      st_bf8(b.p_lo + o + i, sub4(p0, h0), sub4(p1, h1));
+    }
+  }
+  if (lane == 0) b.rz[j] = rz_new;
+}
+
 template <bool REG>
 __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const int* __restrict__ n_dev, int T, int ld,
                                                                int last) {
@@ -223,7 +299,8 @@ int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cu
   if (n <= 0) return VGM_OK;
   // reads acc32 4, s16 2, r32 4, (p_hi, p_lo 4); writes p_hi, p_lo 4
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * (first ? 14.0 : 18.0), s);
-  if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, first);
+  if (T <= 8 * 32 * IR_WG && (T % 8) == 0) ir_dir_warp_kernel<<<ceil_div(n, IR_THREADS / 32), IR_THREADS, 0, s>>>(b, n_dev, n, T, ld, first);
+  else if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, first);
   else ir_dir_kernel<false><<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, first);
   VGM_LAUNCH_OK();
   return VGM_OK;

@@ -1,0 +1,308 @@
+// Tiny dependency levels (one or a few systems, e.g. the wrap-around state of Lorenz96 or every level of an
+// all-hidden chain): one CTA solves one system (M + diag Lambda_u) x_u = rhs_u from start to finish.
+//
+// The batched solver of sweep.cu needs ~190 dependent kernel launches per level no matter how few rows it
+// has; here the same mixed-precision refinement runs inside a single kernel:
+//   factor    FP32 banded Cholesky of A = M_b + diag(Lambda), M_b = M truncated to |i-j| <= 63 (the operators of
+//             the hot path are numerically banded; the caller checks that the 2^-20 band of M fits).  Right-looking,
+//             the 64 x 64 lower-triangular window lives in REGISTERS (16 entries per thread, thread (ti, tk) owns the
+//             window entries with row = ti, col = tk mod 16), one __syncthreads per column, new rows of A arrive
+//             through a prefetched shared-memory ring, columns of L go to an L2-resident scratch; the forward
+//             substitution of the first correction is fused into the factorisation.
+//   refine    r = rhs - M x - Lambda o x in FP64 (exact band of M), d = L^-T L^-1 (r / |r|) in FP32, x += |r| d,
+//             until |r| <= tol |rhs| (each pass contracts the error by ~1e-5: 3 passes reach 1e-13).
+// proxies_for_ode_parameters_and_states.py:262 solves the same system with LAPACK gesv.
+#include "vgm_common.cuh"
+#include "vgm_profile.cuh"
+#include "small_solve.cuh"
+
+namespace vgm {
+
+constexpr int SB = 64;                    // window size = factor half band width + 1
+constexpr int SB_THREADS = 256;           // 16 x 16 owner grid
+constexpr int SB_RING = 32;               // rows of A staged ahead of the factorisation
+constexpr int SB_LBLK = 64;               // columns of L staged per substitution block
+
+struct SmallSmem {
+  double *x, *rhs, *lam, *r64;            // [Tp]
+  float *rv, *yv;                         // [Tp + SB]  (yv has SB floats of zero padding on BOTH sides)
+  float* rdiag;                           // [Tp] 1 / L_jj
+  float* ring;                            // [SB_RING][SB]
+  float* col;                             // [2][SB]
+  float* lbuf;                            // [2 * SB_LBLK][SB]: column j of L at slot j mod 128
+};
+
+__host__ __device__ inline size_t small_smem_bytes(int T) {
+  const size_t Tp = (size_t)(T + 1) & ~(size_t)1;
+  return 4 * Tp * sizeof(double) + (3 * Tp + 3 * SB) * sizeof(float) + (SB_RING * SB + 2 * SB + 2 * SB_LBLK * SB) * sizeof(float);
+}
+
+// A[r][c] of the factored (band-truncated) matrix, c <= r
+__device__ __forceinline__ float small_a(const double* __restrict__ M, const double* lam, int ld, int T, int r, int c) {
+  if (r >= T || c < 0) return 0.f;
+  const double v = M[(size_t)r * ld + c];
+  return (float)(r == c ? v + lam[r] : v);
+}
+
+__global__ void __launch_bounds__(SB_THREADS, 1) small_band_solve_kernel(SmallSolveArgs a) {
+  extern __shared__ double sb_smem[];
+  __shared__ double red[40];
+  const int T = a.T, ld = a.ld;
+  const int Tp = (T + 1) & ~1;
+  SmallSmem s;
+  s.x = sb_smem; s.rhs = s.x + Tp; s.lam = s.rhs + Tp; s.r64 = s.lam + Tp;
+  s.rv = reinterpret_cast<float*>(s.r64 + Tp); s.yv = s.rv + Tp + SB + SB;   // yv[-SB .. Tp + SB)
+  s.rdiag = s.yv + Tp + SB; s.ring = s.rdiag + Tp; s.col = s.ring + SB_RING * SB; s.lbuf = s.col + 2 * SB;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ti = tid >> 4, tk = tid & 15;
+  const int slot = a.rows[blockIdx.x];
+  const size_t so = (size_t)slot * ld;
+  double* xg = a.X + (size_t)a.slot_state[slot] * ld;
+  float* Lg = a.Lscratch + (size_t)blockIdx.x * T * SB;
+  const double* __restrict__ M = a.M;
+
+  if (a.slot_has_self && !a.slot_has_self[slot]) {   // alias quirk, proxies...py:201,245: x = rhs / (2 Lambda)
+    for (int t = tid; t < T; t += SB_THREADS) xg[t] = a.rhs[so + t] / (2.0 * a.Lambda[so + t]);
+    if (tid == 0) { a.done[slot] = 1; a.iters[slot] = 0; a.status[blockIdx.x] = 0; }
+    return;
+  }
+  double bb = 0.0;
+  for (int t = tid; t < T; t += SB_THREADS) {
+    const double b = a.rhs[so + t];
+    s.x[t] = xg[t]; s.rhs[t] = b; s.lam[t] = a.Lambda[so + t];
+    bb += b * b;
+  }
+  for (int t = T + tid; t < Tp + SB; t += SB_THREADS) { s.rv[t] = 0.f; s.yv[t] = 0.f; }
+  if (tid < SB) s.yv[-1 - tid] = 0.f;
+  bb = block_sum(bb, red);
+  if (bb == 0.0) {
+    for (int t = tid; t < T; t += SB_THREADS) xg[t] = 0.0;
+    if (tid == 0) { a.done[slot] = 1; a.iters[slot] = 0; a.status[blockIdx.x] = 0; }
+    return;
+  }
+  const int bandM = a.band_M > 0 ? a.band_M : T;
+
+  int status = 1;                                   // not converged (yet)
+  int pass = 0;
+  for (; pass <= a.max_pass; ++pass) {
+    // ---- FP64 residual: one warp per row, lanes across the band -------------------------------------------
+    for (int m0 = 4 * warp; m0 < T; m0 += 4 * (SB_THREADS / 32)) {     // four rows at a time: their loads overlap
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const int kmin = max(0, m0 - bandM), kmax = min(T - 1, m0 + 3 + bandM);
+      for (int k = kmin + lane; k <= kmax; k += 32) {
+        const double xk = s.x[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = m0 + q;
+          if (m < T && k >= m - bandM && k <= m + bandM) acc[q] = fma(M[(size_t)m * ld + k], xk, acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double v = warp_sum(acc[q]);
+        const int m = m0 + q;
+        if (lane == 0 && m < T) s.r64[m] = s.rhs[m] - v - s.lam[m] * s.x[m];
+      }
+    }
+    __syncthreads();
+    double rr = 0.0;
+    for (int t = tid; t < T; t += SB_THREADS) rr += s.r64[t] * s.r64[t];
+    rr = block_sum(rr, red);
+    if (rr <= a.tol * a.tol * bb) { status = 0; break; }
+    if (pass == a.max_pass) break;
+    const double sigma = sqrt(rr), isig = 1.0 / sigma;
+    for (int t = tid; t < T; t += SB_THREADS) s.rv[t] = (float)(s.r64[t] * isig);
+    __syncthreads();
+
+    if (pass == 0) {
+      // ================= factorisation fused with the first forward substitution =================
+      float w[4][4];
+#pragma unroll
+      for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+        for (int ic = 0; ic < 4; ++ic) {
+          const int r = ia * 16 + ti, c = ic * 16 + tk;
+          w[ia][ic] = (c <= r) ? small_a(M, s.lam, ld, T, r, c) : 0.f;
+        }
+      for (int idx = tid; idx < 16 * SB; idx += SB_THREADS) {          // ring rows 64..79
+        const int r = SB + idx / SB, c = r - (SB - 1) + idx % SB;
+        s.ring[(r & (SB_RING - 1)) * SB + (c & (SB - 1))] = small_a(M, s.lam, ld, T, r, c);
+      }
+      __syncthreads();
+      bool failed = false;
+      for (int j0 = 0; j0 < T && !failed; j0 += 16) {
+        // rows j0+80 .. j0+95 are needed in the NEXT block of 16 columns: issue their loads now
+        double pf[4];
+        int pslot[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = tid + e * SB_THREADS;
+          const int r = j0 + SB + 16 + idx / SB, c = r - (SB - 1) + idx % SB;
+          pslot[e] = (r & (SB_RING - 1)) * SB + (c & (SB - 1));
+          pf[e] = (r < T && c >= 0) ? M[(size_t)r * ld + c] + (c == r ? s.lam[r] : 0.0) : 0.0;
+        }
+        const int j1 = min(j0 + 16, T);
+        for (int j = j0; j < j1; ++j) {
+          const int jm = j & (SB - 1);
+          float* col = s.col + (j & 1) * SB;
+          // phase A: the owners of window column j publish it (offset = row - j)
+          if (tk == (jm & 15)) {
+            const int cs = jm >> 4;
+#pragma unroll
+            for (int ia = 0; ia < 4; ++ia) {
+              const int off = (ia * 16 + ti - jm) & (SB - 1);
+#pragma unroll
+              for (int ic = 0; ic < 4; ++ic)
+                if (ic == cs) col[off] = w[ia][ic];
+            }
+          }
+          __syncthreads();
+          // phase B: scale the column, rank-1 update of the trailing window, emit L, forward substitution
+          const float piv = col[0];
+          if (!(piv > 0.f)) { failed = true; break; }                     // uniform: every thread reads the same value
+          const float inv = rsqrtf(piv), d = piv * inv;   // 2-ulp reciprocal square root: the refinement absorbs it
+          float lr[4], lc[4];
+          int offr[4], offc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            offr[q] = (q * 16 + ti - jm) & (SB - 1);
+            offc[q] = (q * 16 + tk - jm) & (SB - 1);
+            lr[q] = col[offr[q]] * inv;
+            lc[q] = col[offc[q]] * inv;
+          }
+#pragma unroll
+          for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic)
+              if (offc[ic] >= 1 && offc[ic] <= offr[ia] && j + offr[ia] < T) w[ia][ic] = fmaf(-lr[ia], lc[ic], w[ia][ic]);
+          if (tid < SB) {
+            const int i = tid;
+            const bool ok = j + i < T;
+            const float li = (i == 0) ? d : col[i] * inv;
+            Lg[(size_t)j * SB + i] = ok ? li : 0.f;
+            const float yj = s.rv[j] * inv;
+            if (i == 0) { s.yv[j] = yj; s.rdiag[j] = inv; }
+            else if (ok) s.rv[j + i] -= li * yj;
+          }
+          // row j + 64 enters the window in the row slot that row j leaves
+          if (ti == (jm & 15)) {
+            const int as = jm >> 4, r = j + SB;
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic) {
+              const float v = (r < T) ? s.ring[(r & (SB_RING - 1)) * SB + ic * 16 + tk] : 0.f;
+#pragma unroll
+              for (int ia = 0; ia < 4; ++ia)
+                if (ia == as) w[ia][ic] = v;
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s.ring[pslot[e]] = (float)pf[e];
+      }
+      if (failed) { status = 2; break; }
+      __syncthreads();
+    } else {
+      // ================= forward substitution with the stored factor: L y = rv =================
+      // column-oriented: y_j = rv_j / L_jj, then rv[j+i] -= L[j+i][j] y_j (no reductions on the critical path);
+      // warps 1..7 stage the next 64 columns of L while warp 0 runs the recurrence
+      const int nblk = (T + SB_LBLK - 1) / SB_LBLK;
+      for (int idx = tid; idx < SB_LBLK * SB; idx += SB_THREADS) s.lbuf[idx] = (idx / SB < T) ? Lg[idx] : 0.f;
+      for (int blk = 0; blk < nblk; ++blk) {
+        __syncthreads();
+        if (warp > 0) {
+          if (blk + 1 < nblk) {
+            float* nxt = s.lbuf + ((blk + 1) & 1) * SB_LBLK * SB;
+            const int base = (blk + 1) * SB_LBLK;
+            for (int idx = tid - 32; idx < SB_LBLK * SB; idx += SB_THREADS - 32)
+              nxt[idx] = (base + idx / SB < T) ? Lg[(size_t)base * SB + idx] : 0.f;
+          }
+        } else {
+          const int jend = min(T, (blk + 1) * SB_LBLK);
+          for (int j = blk * SB_LBLK; j < jend; ++j) {
+            const float* L = s.lbuf + (j & (2 * SB_LBLK - 1)) * SB;
+            const float yj = s.rv[j] * s.rdiag[j];
+            if (lane == 0) s.yv[j] = yj;
+            s.rv[j + 1 + lane] -= L[1 + lane] * yj;                     // i = 1..32   (L is zero past the end)
+            if (lane < SB - 33) s.rv[j + 33 + lane] -= L[33 + lane] * yj;   // i = 33..63
+            __syncwarp();
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ================= backward substitution: L^T d = y (in place in yv) =================
+    // also column-oriented, using ROWS of L gathered from the 128-column circular buffer:
+    //   d_j = y_j / L_jj, then y[j-i] -= L[j][j-i] d_j  with  L[j][j-i] = column (j-i), entry i
+    {
+      const int nblk = (T + SB_LBLK - 1) / SB_LBLK;
+      // block nblk-1 (and nblk-2 for the rows that reach back into it) must be resident
+      for (int bq = max(0, nblk - 2); bq < nblk; ++bq) {
+        const int base = bq * SB_LBLK;
+        float* dst = s.lbuf + (bq & 1) * SB_LBLK * SB;
+        for (int idx = tid; idx < SB_LBLK * SB; idx += SB_THREADS)
+          dst[idx] = (base + idx / SB < T) ? Lg[(size_t)base * SB + idx] : 0.f;
+      }
+      for (int blk = nblk - 1; blk >= 0; --blk) {
+        __syncthreads();
+        // rows of block blk read columns of blocks blk and blk-1; block blk-2 is staged (into the half that held
+        // block blk) only after this block is done, so stage it for the NEXT iteration at the end instead
+        if (warp == 0) {
+          const int jbeg = blk * SB_LBLK;
+          for (int j = min(T, jbeg + SB_LBLK) - 1; j >= jbeg; --j) {
+            const float dj = s.yv[j] * s.rdiag[j];
+            if (lane == 0) s.yv[j] = dj;
+            {
+              const int i = 1 + lane, c = j - i;                        // i = 1..32
+              if (c >= 0) s.yv[c] -= s.lbuf[(c & (2 * SB_LBLK - 1)) * SB + i] * dj;
+            }
+            if (lane < SB - 33) {
+              const int i = 33 + lane, c = j - i;                       // i = 33..63
+              if (c >= 0) s.yv[c] -= s.lbuf[(c & (2 * SB_LBLK - 1)) * SB + i] * dj;
+            }
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        if (blk >= 2) {                                                 // block blk-2 replaces block blk
+          const int base = (blk - 2) * SB_LBLK;
+          float* dst = s.lbuf + (blk & 1) * SB_LBLK * SB;
+          for (int idx = tid; idx < SB_LBLK * SB; idx += SB_THREADS) dst[idx] = Lg[(size_t)base * SB + idx];
+        }
+      }
+      __syncthreads();
+    }
+    for (int t = tid; t < T; t += SB_THREADS) s.x[t] += sigma * (double)s.yv[t];
+    __syncthreads();
+  }
+
+  if (status == 0)
+    for (int t = tid; t < T; t += SB_THREADS) xg[t] = s.x[t];
+  if (tid == 0) {
+    a.status[blockIdx.x] = status;
+    a.iters[slot] = pass;
+    if (status == 0) a.done[slot] = 1;
+  }
+}
+
+size_t small_solve_scratch_bytes(int T) { return align_up((size_t)SMALL_SOLVE_MAX_SYSTEMS * T * SB * sizeof(float), 256) + 256; }
+
+bool small_solve_applicable(const vgm_operators* ops, int ruu_const, int n_rows, int T) {
+  return ruu_const && ops->M && n_rows > 0 && n_rows <= SMALL_SOLVE_MAX_SYSTEMS && T >= SB &&
+         ops->band_M_lp > 0 && ops->band_M_lp < SB && small_smem_bytes(T) <= 200 * 1024;
+}
+
+int small_solve(const SmallSolveArgs& args, int n_sys, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    VGM_CUDA_OK(cudaFuncSetAttribute(small_band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  ProfScope prof(PROF_VEC, 0.0, 0.0, s);
+  small_band_solve_kernel<<<n_sys, SB_THREADS, small_smem_bytes(args.T), s>>>(args);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+}  // namespace vgm

@@ -19,6 +19,7 @@
 #include "vgm_profile.cuh"
 #include "tc_gemm.cuh"
 #include "refine.cuh"
+#include "small_solve.cuh"
 
 struct vgm_program;
 
@@ -243,6 +244,7 @@ __global__ void add_live_terms_kernel(const int* __restrict__ live_pair_slot, co
 struct PcgWs {
   CgBuf cb;
   IrBuf ir;                      // low-precision side of the mixed-precision solver
+  float* small_scratch;          // factor scratch of the tiny-level solver (+ 64 status ints at its end)
   int* host_poll_dev;            // 2 ints
 };
 
@@ -251,7 +253,8 @@ static size_t pcg_ws_bytes(int n_hidden, int T, int ld) {
   const int n_tiles = ceil_div(T, 64);  // upper bound over GEMM configurations
   const size_t part = align_up((size_t)n_hidden * n_tiles * sizeof(double), 256);
   const size_t vec = align_up((size_t)n_hidden * sizeof(double), 256);
-  return 5 * mat + ir_ws_bytes(n_hidden, ld) + 2 * part + 3 * vec + 4 * vec /*done, iters, act x2 (ints fit)*/ + 1024;
+  return 5 * mat + ir_ws_bytes(n_hidden, ld) + small_solve_scratch_bytes(T) + 2 * part + 3 * vec +
+         4 * vec /*done, iters, act x2 (ints fit)*/ + 1024;
 }
 
 static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, PcgWs& w) {
@@ -269,6 +272,7 @@ static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, Pcg
   c.Z = (double*)p; p += mat;
   c.W = (double*)p; p += mat;
   ir_carve(p, n_hidden, ld, w.ir);
+  w.small_scratch = (float*)p; p += small_solve_scratch_bytes(T);
   c.pq_part = (double*)p; p += part;
   c.rz_part = (double*)p; p += part;
   c.rz = (double*)p; p += vec;
@@ -616,6 +620,44 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
   VGM_REQUIRE(ops && ops->D && ops->DT, "operators D and DT are required");
   VGM_REQUIRE(!ruu_const || ops->M, "shared operator M is required when R_uu is constant");
   VGM_REQUIRE(ruu_const || Ruu, "R_uu array is required when it is not constant");
+  // a handful of systems (the wrap-around state, a level of an all-hidden chain): one CTA per system does the
+  // whole banded-Cholesky + refinement solve in a single launch
+  if (opts && opts->small_level_solver && ops->M_bf16x2 && small_solve_applicable(ops, ruu_const, n_rows, T)) {
+    SmallSolveArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.M = ops->M; sa.T = T; sa.ld = ld; sa.band_M = ops->band_M;
+    sa.Lambda = Lambda; sa.rhs = rhs; sa.X = X; sa.slot_state = slot_state; sa.slot_has_self = slot_has_self;
+    sa.rows = rows; sa.Lscratch = w.small_scratch;
+    sa.tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
+    sa.max_pass = 8;
+    sa.done = w.cb.done; sa.iters = w.cb.iters;
+    sa.status = (int*)((char*)w.small_scratch + small_solve_scratch_bytes(T) - 256);
+    cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
+    if (g_debug) { cudaEventCreate(&dbg0); cudaEventCreate(&dbg1); cudaEventRecord(dbg0, s); }
+    VGM_TRY(small_solve(sa, n_rows, s));
+    if (g_debug) cudaEventRecord(dbg1, s);
+    int st[SMALL_SOLVE_MAX_SYSTEMS];
+    VGM_CUDA_OK(cudaMemcpyAsync(st, sa.status, n_rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGM_CUDA_OK(cudaStreamSynchronize(s));
+    cnt.launches += 1;
+    bool ok = true;
+    for (int i = 0; i < n_rows; ++i) ok = ok && st[i] == 0;
+    if (g_debug) {
+      int h_rows0 = 0, h_it = -1;
+      cudaMemcpy(&h_rows0, rows, sizeof(int), cudaMemcpyDeviceToHost);
+      cudaMemcpy(&h_it, w.cb.iters + h_rows0, sizeof(int), cudaMemcpyDeviceToHost);
+      float dbg_ms = 0.f;
+      cudaEventElapsedTime(&dbg_ms, dbg0, dbg1);
+      cudaEventDestroy(dbg0); cudaEventDestroy(dbg1);
+      fprintf(stderr, "[vgm] tiny level: %d system(s), single-CTA solver %s (status %d, %d passes, %.3f ms)\n", n_rows,
+              ok ? "converged" : "fell back", st[0], h_it, dbg_ms);
+    }
+    if (ok) {
+      if (info) info->iterations = max(info->iterations, 1);
+      return VGM_OK;
+    }
+    // fall through to the batched solver (x was left untouched for the systems that did not converge)
+  }
   // mixed precision needs the bf16 operators and tiles that the TMA boxes (128 x 64) fit into
   if (ruu_const && ops->G_bf16 && ops->M_bf16x2 && T >= 128)
     return ir_solve(ops, Lambda, rhs, X, slot_state, slot_has_self, rows, n_rows, T, ld, opts, w, info, cnt, s);

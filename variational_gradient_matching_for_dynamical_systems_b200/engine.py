@@ -191,7 +191,7 @@ class VGMEngine:
         on the tcgen05 tensor cores (bf16-split operands); 'pcg' = FP64 preconditioned CG only;
         'auto' = 'mixed' whenever the model allows it (R_uu constant, T >= MIXED_MIN_T).
     """
-    MIXED_MIN_T = 64
+    MIXED_MIN_T = 128
     # preconditioner S G S of the mixed-precision solver: G = (M + SHIFT_FRAC mean(Lambda) I)^-1,
     # S = diag sqrt((shift + c) / (Lambda + c)), c = SCALE_FRAC mean(Lambda); spec(S G S A) then has a
     # condition number of ~6-7 instead of ~20 for the plain shifted inverse (Lorenz96, C3/C5 of BASELINE.json)
@@ -199,7 +199,8 @@ class VGMEngine:
 
     def __init__(self, model: OdeModel, D, A=None, hidden=None, couplings=None, schedule="reference",
                  theta_mode="reference", theta_literal=(8.0,), tol=1e-13, max_iter=0, check_every=8,
-                 precondition=True, solver="auto", inner_iters=10, optimistic_passes=4, prefer_builtin=True,
+                 precondition=True, solver="auto", inner_iters=10, optimistic_passes=4, small_level_solver=False,
+                 prefer_builtin=True,
                  device=None, problem=None):
         self.lib = _lib.load()
         self.dev = device or _lib.require_cuda()
@@ -232,7 +233,8 @@ class VGMEngine:
         if solver == "mixed" and not can_mix:
             raise ValueError("solver='mixed' needs constant R_uu, precondition=True and T >= %d" % self.MIXED_MIN_T)
         self.solver = "mixed" if (solver in ("auto", "mixed") and can_mix) else "pcg"
-        self.opts = _lib.SolverOpts(tol, max_iter, check_every, int(inner_iters), int(optimistic_passes))
+        self.opts = _lib.SolverOpts(tol, max_iter, check_every, int(inner_iters), int(optimistic_passes),
+                                    1 if small_level_solver else 0)
         self.X = torch.zeros((self.K, self.ld), dtype=torch.float64, device=self.dev)
         self.DX = torch.zeros_like(self.X)
         self.theta = torch.zeros(max(self.p, 1), dtype=torch.float64, device=self.dev)
