@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--inner-iters", type=int, default=10)
     ap.add_argument("--tol", type=float, default=1e-13)
     ap.add_argument("--optimistic-passes", type=int, default=4)
+    ap.add_argument("--pipeline-chunks", type=int, default=3, help="e2e: state ranges whose copies overlap the compute")
     ap.add_argument("--no-profile", action="store_true", help="skip the second, per-kernel-instrumented timed region")
     return ap.parse_args()
 
@@ -283,7 +284,7 @@ def native_arm(args):
                 th_h.copy_(core.theta, non_blocking=True)
                 torch.cuda.synchronize()
             else:
-                core.iteration_host(Xh_in, th_h, Xh_out, updated_rows_only=True)
+                core.iteration_host(Xh_in, th_h, Xh_out, updated_rows_only=True, pipeline_chunks=args.pipeline_chunks)
 
         e2e_step()
         barrier()
@@ -300,7 +301,8 @@ def native_arm(args):
             dt = float(tmax.item())
         e2e = {"value": n_hidden_total * T * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
-               "api": "vgm_iteration_host (C ABI, pinned host buffers)" if world == 1 else
+               "api": ("vgm_iteration_host (C ABI, pinned host buffers; %d state ranges pipelined: copy-in, "
+                       "solve and copy-out overlap)" % core.last_pipeline) if world == 1 else
                       "DistributedVGMEngine.iteration with pinned host copies per rank"}
 
     if rank != 0:

@@ -285,6 +285,22 @@ typedef struct {
    * (i < out_n_rows) and only those are copied back to the host (one strided copy); the rows of states that the
    * sweep does not touch (observed + clamped, proxies...py:175-179) are then left as they are in X_host_out. */
   int out_row0, out_row_stride, out_n_rows;
+  /* vgm_iteration_host only, optional pipelining of the host<->device copies with the compute (pipe_chunks >= 2).
+   * The states are cut into pipe_chunks contiguous ranges [pipe_state_ptr_host[c], ..[c+1]) (boundaries multiples
+   * of 8); range c is copied in, then STAGED (D.X, theta partial sums, coefficients, rhs GEMM for its hidden slots
+   * [pipe_slot_ptr_host[c], ..[c+1])), then the systems of dependency level 0 whose state lies in
+   * [state_ptr[c] - halo_x, state_ptr[c+1] - halo_x) are SOLVED (positions [pipe_row_ptr_host[c], ..[c+1]) of the
+   * level, hidden slots [pipe_out_slot_ptr_host[c], ..[c+1])) and copied out while the next range is in flight.
+   * The shift by the halo keeps every coefficient on the sweep-start snapshot (proxies...py:191).  Row/slot ranges
+   * start at the "seam" (states < halo_x, which the last range reads cyclically): rows [0, row_ptr[0]) are solved
+   * last; every slot of a later level lies in the last range.  Coefficients of a state read X rows within
+   * +-pipe_halo_x (cyclically) and D.X rows within +-pipe_halo_dx.  Requires theta_mode 0, ODE row j == state j,
+   * hidden slots in ascending state order (VGMEngine.iteration_host checks all of it and falls back otherwise). */
+  int pipe_chunks, pipe_halo_x, pipe_halo_dx;
+  const int* pipe_state_ptr_host;
+  const int* pipe_slot_ptr_host;
+  const int* pipe_row_ptr_host;
+  const int* pipe_out_slot_ptr_host;
 } vgm_model_tables;
 size_t vgm_iteration_ws_bytes(const vgm_model_tables* model, const vgm_sweep_plan* plan);
 int vgm_iteration_device(const vgm_program* prog, const vgm_model_tables* model, const vgm_sweep_plan* plan,

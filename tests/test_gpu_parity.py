@@ -351,6 +351,38 @@ def test_host_buffer_iteration_matches_reference_golden(pkg, rows_only):
     assert relerr(out[:, :eng.T].numpy().T, g["states"][0]) < TOL
 
 
+@pytest.mark.parametrize("rows_only", [False, True])
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_pipelined_host_iteration_matches_plain_and_oracle(pkg, chunks, rows_only):
+    """vgm_iteration_host with the copies pipelined against the compute (chunked states, coefficients assembled one
+    chunk ahead, the cyclic seam solved last): identical theta (same partial-sum layout) and states to 1e-12 of the
+    unpipelined call, 1e-9 of the oracle."""
+    p, _lib, engine = pkg
+    K, T = 96, 160
+    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=21)
+    rng = np.random.default_rng(22)
+    X0 = Xtrue.copy()
+    X0[:, 1::2] += 0.5 * rng.standard_normal((T, K // 2))
+    D, A, *_ = vo.kernel_function(t, t, "rbf", [0.0625, 1.0])
+    hidden = list(range(1, K, 2))
+    Xref = vo.lorenz96_state_sweep(X0, 8.0, D, hidden)
+    th_ref = vo.lorenz96_theta_step(X0, D)[0]
+    eng = engine.VGMEngine(p.OdeModel.lorenz96(K), D, A, hidden=hidden)
+    Xh = torch.zeros((eng.K, eng.ld), dtype=torch.float64).pin_memory()
+    Xh[:, :T] = torch.from_numpy(np.ascontiguousarray(X0.T))
+    res = {}
+    for n in (0, chunks):
+        out = Xh.clone().pin_memory()
+        th = torch.zeros(1, dtype=torch.float64).pin_memory()
+        eng.iteration_host(Xh, th, out, updated_rows_only=rows_only, pipeline_chunks=n)
+        assert eng.last_pipeline == n
+        res[n] = (out[:, :T].numpy().T.copy(), th.numpy().copy())
+        assert relerr(res[n][1], [th_ref]) < TOL
+        assert relerr(res[n][0], Xref) < TOL
+    assert relerr(res[chunks][1], res[0][1]) < 1e-15
+    assert relerr(res[chunks][0], res[0][0]) < 1e-11
+
+
 @pytest.mark.parametrize("fname", ["lotka_volterra_T50.npz", "lorenz_attractor_T150.npz",
                                    "protein_transduction_T99.npz"])
 def test_multi_parameter_models_vs_patched_reference_golden(pkg, fname):

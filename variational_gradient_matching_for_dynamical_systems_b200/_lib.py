@@ -74,7 +74,10 @@ class ModelTables(C.Structure):
     _fields_ = [("n_states", C.c_int), ("n_odes", C.c_int), ("n_param", C.c_int),
                 ("ode_class", c_ip), ("ode_idx", c_ip), ("ode_state", c_ip),
                 ("theta_mode", C.c_int), ("theta_literal", C.c_double * 8),
-                ("out_row0", C.c_int), ("out_row_stride", C.c_int), ("out_n_rows", C.c_int)]
+                ("out_row0", C.c_int), ("out_row_stride", C.c_int), ("out_n_rows", C.c_int),
+                ("pipe_chunks", C.c_int), ("pipe_halo_x", C.c_int), ("pipe_halo_dx", C.c_int),
+                ("pipe_state_ptr_host", C.POINTER(C.c_int)), ("pipe_slot_ptr_host", C.POINTER(C.c_int)),
+                ("pipe_row_ptr_host", C.POINTER(C.c_int)), ("pipe_out_slot_ptr_host", C.POINTER(C.c_int))]
 
 
 # name -> (restype, argtypes); every symbol declared in include/vgm_b200.h

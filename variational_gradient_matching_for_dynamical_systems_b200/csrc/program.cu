@@ -249,6 +249,23 @@ extern "C" size_t vgm_param_stats_ws_bytes(int n_odes, int T, int n_param) {
   return align_up((size_t)ceil_div(n_odes, 8) * nstat * sizeof(double), 256);
 }
 
+namespace vgm {
+// ODE rows [j0, j1) only (j0 a multiple of 8): partials land where the full launch would put them, so a later
+// param_stats_reduce over all of them gives bit-identical statistics.
+int param_stats_range(const vgm_program* prog, const double* X, const double* DX, int ld, int T, int j0, int j1,
+                      const int* ode_class, const int* ode_idx, const int* ode_state, double* partial, cudaStream_t s) {
+  if (j1 <= j0) return VGM_OK;
+  const int nstat = prog->n_param + prog->n_param * (prog->n_param + 1) / 2;
+  return program_param_stats(prog, X, DX, ld, T, j1 - j0, ode_class + j0, ode_idx + (size_t)j0 * prog->arity,
+                             ode_state + j0, partial + (size_t)(j0 / 8) * nstat, s);
+}
+int param_stats_reduce(const vgm_program* prog, const double* partial, int n_odes, double* stats, cudaStream_t s) {
+  stats_reduce_kernel<<<1, 256, 0, s>>>(partial, ceil_div(n_odes, 8), prog->n_param, stats);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+}  // namespace vgm
+
 extern "C" int vgm_param_stats(const vgm_program* prog, const double* X, const double* DX, int ld, int T, int n_odes,
                                const int* ode_class, const int* ode_idx, const int* ode_state, double* stats,
                                void* ws, size_t ws_bytes, vgm_stream_t stream) {

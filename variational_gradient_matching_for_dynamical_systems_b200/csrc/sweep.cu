@@ -777,6 +777,53 @@ static int state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* pl
   return VGM_OK;
 }
 
+// Phase 1 for the hidden slots [s0, s1) only (pipelined host iteration: rows arrive chunk by chunk).
+int state_sweep_prepare_range(const vgm_program* prog, const vgm_sweep_plan* pl, const vgm_operators* ops,
+                              const double* X, const double* DX0, const double* theta_star, int s0, int s1, void* ws,
+                              size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+  VGM_REQUIRE(prog && pl && ops && X && DX0 && theta_star && 0 <= s0 && s0 <= s1 && s1 <= pl->n_hidden, "slot range");
+  if (s1 == s0) return VGM_OK;
+  SweepWs w;
+  VGM_TRY(sweep_carve(ws, ws_bytes, pl, w));
+  const int T = pl->T, ld = pl->ld;
+  const size_t o = (size_t)s0 * ld;
+  vgm_sweep_plan sub = *pl;
+  sub.n_hidden = s1 - s0;
+  sub.pair_ptr = pl->pair_ptr + s0;
+  VGM_TRY(program_state_assemble(prog, &sub, X, DX0, theta_star, w.Lambda + o, w.rhs + o, w.ruu + o,
+                                 w.Ruu ? w.Ruu + o : nullptr, w.Rlive, s));
+  vgm_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = w.ruu + o; g.B = ops->DT; g.C = w.rhs + o; g.C0 = w.rhs + o;
+  g.lda = g.ldb = g.ldc = ld;
+  g.N = s1 - s0; g.M = T; g.K = T;
+  g.alpha = 1.0; g.beta = 1.0;
+  g.U1 = pl->ruu_const ? nullptr : w.Ruu + o;
+  g.V1 = w.ruu + o;
+  g.g1 = pl->ruu_const ? -pl->ruu_value : -1.0;
+  g.band = ops->band_D;
+  VGM_TRY(dgemm_nt(g, s));
+  if (info) { info->gemm_calls += 1; info->kernel_launches += 2; }
+  return VGM_OK;
+}
+
+// Solve rows [r0, r1) of dependency level `lev` (positions within the level); no live-term refresh, so only
+// meaningful for level 0 or after state_sweep_level has patched the right-hand sides.
+int state_sweep_level_rows(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts, double* X,
+                           int lev, int r0, int r1, void* ws, size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+  VGM_REQUIRE(pl && ops && X && lev >= 0 && lev < pl->n_levels, "level out of range");
+  const int base = pl->level_ptr_host[lev], n_lev = pl->level_ptr_host[lev + 1] - base;
+  VGM_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= n_lev, "row range");
+  if (r1 == r0) return VGM_OK;
+  SweepWs w;
+  VGM_TRY(sweep_carve(ws, ws_bytes, pl, w));
+  Counters cnt;
+  int rc = pcg_solve(ops, pl->ruu_const, w.Ruu, w.Lambda, w.rhs, X, pl->slot_state, pl->slot_has_self,
+                     pl->level_slots + base + r0, r1 - r0, pl->n_hidden, pl->T, pl->ld, opts, w.pcg, info, cnt, s);
+  if (info) { info->gemm_calls += cnt.gemm; info->kernel_launches += cnt.launches; }
+  return rc;
+}
+
 // Phase 2, once per dependency level (in order): refresh D x_k of the states updated in the
 // previous level that this level reads live (:225), patch rhs, solve the level's systems.
 static int state_sweep_level(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts,
@@ -819,6 +866,11 @@ static int state_sweep_level(const vgm_sweep_plan* pl, const vgm_operators* ops,
     info->kernel_launches += cnt.launches;
   }
   return rc;
+}
+
+int state_sweep_level_full(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts, double* X,
+                           int lev, void* ws, size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+  return state_sweep_level(pl, ops, opts, X, lev, ws, ws_bytes, info, s);
 }
 
 static int state_sweep(const vgm_program* prog, const vgm_sweep_plan* pl, const vgm_operators* ops,

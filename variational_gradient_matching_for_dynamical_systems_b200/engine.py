@@ -258,6 +258,8 @@ class VGMEngine:
         self.ws = torch.empty(n_ws, dtype=torch.uint8, device=self.dev)
         self.info = _lib.SweepInfo()
         self.last_info = None
+        self._pipe_cache = {}
+        self.last_pipeline = 0
 
     # ---- data movement ---------------------------------------------------------------------
     def set_states(self, X_TK):
@@ -399,15 +401,67 @@ class VGMEngine:
         _lib.check(rc, allow_notconv=allow_unconverged)
         return self.last_info
 
+    def _pipeline_tables(self, n_chunks):
+        """Chunk description for the pipelined ``vgm_iteration_host`` (vgm_model_tables.pipe_*), or None when the
+        model / plan does not allow it (see the conditions in include/vgm_b200.h)."""
+        K, hp, prob = self.K, self.problem.host_plan, self.problem
+        hidden = np.asarray(hp.slot_state, dtype=np.int64)
+        if (n_chunks < 2 or self.theta_mode != "reference" or prob.n_stats_odes != K or prob.n_odes != K
+                or hp.n_hidden < 2 or np.any(np.diff(hidden) <= 0)
+                or not np.array_equal(prob.ode_state, np.arange(K))):
+            return None
+        arity = int(np.asarray(prob.ode_idx).size) // max(prob.n_odes, 1)
+
+        def cyc(d):
+            d = np.abs(d) % K
+            return np.minimum(d, K - d)
+        h = int(cyc(np.asarray(prob.ode_idx).reshape(K, arity).astype(np.int64) - np.arange(K)[:, None]).max()) if arity else 0
+        pair_slot = np.repeat(np.arange(hp.n_hidden), np.diff(hp.pair_ptr))
+        hc = int(cyc(hidden[pair_slot] - prob.ode_state[hp.pair_ode].astype(np.int64)).max()) if len(pair_slot) else 0
+        hx, hd = h + hc, hc
+        n_chunks = min(int(n_chunks), 32)
+        kp = (np.round(np.arange(n_chunks + 1) * K / n_chunks / 8).astype(np.int64) * 8)
+        kp[0], kp[-1] = 0, K
+        if np.any(np.diff(kp) < 2 * hx + 8) or hx <= 0:
+            return None
+        lvl0 = np.asarray(hp.level_slots[:hp.level_ptr[1]], dtype=np.int64)
+        later = np.asarray(hp.level_slots[hp.level_ptr[1]:], dtype=np.int64)
+        sp = np.searchsorted(hidden, kp)
+        if np.any(np.diff(lvl0) <= 0) or (len(later) and later.min() < sp[-2]):
+            return None
+        # solve ranges: shifted left by the halo; they start at the seam (states < hx) and end with the level
+        ko = kp - hx
+        ko[0], ko[-1] = hx, K
+        op = np.searchsorted(hidden, ko)
+        rp = np.searchsorted(lvl0, op)
+        rp[-1] = len(lvl0)
+        return dict(n=n_chunks, hx=hx, hd=hd, kp=_host_i32(kp), sp=_host_i32(sp), rp=_host_i32(rp), op=_host_i32(op))
+
     def iteration_host(self, X_host_KT: torch.Tensor, theta_host: torch.Tensor, X_host_out: torch.Tensor = None,
-                       allow_unconverged=False, updated_rows_only=False):
+                       allow_unconverged=False, updated_rows_only=False, pipeline_chunks=0):
         """End-to-end iteration with HOST buffers (vgm_iteration_host): ``X_host_KT`` is a
         (pinned) CPU tensor [K, ld]; the updated proxies go to ``X_host_out`` (default: in
         place); ``theta_host`` a CPU tensor [p].  ``updated_rows_only``: copy back only the rows of the
         hidden states (the others are not changed by the sweep and are left as they are in ``X_host_out``);
-        needs the hidden states to be equally spaced rows, otherwise everything is copied."""
+        needs the hidden states to be equally spaced rows, otherwise everything is copied.
+        ``pipeline_chunks`` >= 2: cut the states into that many ranges and overlap the host->device copy of range
+        c+1 and the device->host copy of range c-1 with the solve of range c (falls back to the plain path when the
+        model does not allow it; ``self.last_pipeline`` tells which ran)."""
         if X_host_out is None:
             X_host_out = X_host_KT
+        if pipeline_chunks and pipeline_chunks not in self._pipe_cache:
+            self._pipe_cache[pipeline_chunks] = self._pipeline_tables(pipeline_chunks)
+        pt = self._pipe_cache.get(pipeline_chunks) if pipeline_chunks else None
+        self.last_pipeline = pt["n"] if pt else 0
+        m = self._mt
+        m.pipe_chunks = 0
+        if pt:
+            m.pipe_chunks, m.pipe_halo_x, m.pipe_halo_dx = pt["n"], pt["hx"], pt["hd"]
+            m.pipe_state_ptr_host = C.cast(pt["kp"], C.POINTER(C.c_int))
+            m.pipe_slot_ptr_host = C.cast(pt["sp"], C.POINTER(C.c_int))
+            m.pipe_row_ptr_host = C.cast(pt["rp"], C.POINTER(C.c_int))
+            m.pipe_out_slot_ptr_host = C.cast(pt["op"], C.POINTER(C.c_int))
+            self._pipe_keep = pt
         self._mt.out_n_rows = 0
         h = self.plan.hidden
         if updated_rows_only and len(h) > 1:
@@ -424,6 +478,7 @@ class VGMEngine:
                                          self.theta.data_ptr(), self.stats.data_ptr(), self.ws.data_ptr(),
                                          self.ws.numel(), C.byref(self.info), _lib.stream_ptr())
         self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
+        m.pipe_chunks = 0
         _lib.check(rc, allow_notconv=allow_unconverged)
         return self.last_info
 
