@@ -99,8 +99,10 @@ int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row
 int vgm_band_halfwidth(const double* B, int rows, int cols, int ld, double rel_threshold, int* band_host,
                        vgm_stream_t stream);
 /* Per-launch CUDA-event timing of the kernel families (used by bench.py for the roofline figures):
- * family 0 = FP64 DMMA GEMM, 1 = tcgen05 BF16 GEMM, 2 = solver vector kernels, 3 = coefficient assembly. */
-enum { VGM_PROF_DGEMM = 0, VGM_PROF_TCGEMM = 1, VGM_PROF_VEC = 2, VGM_PROF_ASSEMBLE = 3 };
+ * family 0 = FP64 DMMA GEMM, 1 = tcgen05 BF16 GEMM, 2 = other solver vector kernels (init / finish / prep),
+ * 3 = coefficient assembly + theta statistics, 4 = ir_update_kernel, 5 = ir_dir_kernel. */
+enum { VGM_PROF_DGEMM = 0, VGM_PROF_TCGEMM = 1, VGM_PROF_VEC = 2, VGM_PROF_ASSEMBLE = 3, VGM_PROF_IR_UPDATE = 4,
+       VGM_PROF_IR_DIR = 5 };
 int vgm_profile_enable(int on);
 int vgm_profile_collect(int family, double* flops, double* bytes, double* ms, long long* launches); /* synchronises */
 int vgm_transpose(const double* in, int ld_in, double* out, int ld_out, int rows, int cols, vgm_stream_t stream);

@@ -298,7 +298,7 @@ int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const d
 int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   // reads acc32 4, s16 2, r32 4, (p_hi, p_lo 4); writes p_hi, p_lo 4
-  ProfScope prof(PROF_VEC, 0.0, (double)n * T * (first ? 14.0 : 18.0), s);
+  ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * (first ? 14.0 : 18.0), s);
   if (T <= 8 * 32 * IR_WG && (T % 8) == 0) ir_dir_warp_kernel<<<ceil_div(n, IR_THREADS / 32), IR_THREADS, 0, s>>>(b, n_dev, n, T, ld, first);
   else if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, first);
   else ir_dir_kernel<false><<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, first);
@@ -309,7 +309,7 @@ int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cu
 int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4, s16 2); writes d32 4, (r32 4, rsb 2)
-  ProfScope prof(PROF_VEC, 0.0, (double)n * T * (last ? 20.0 : 32.0), s);
+  ProfScope prof(PROF_IR_UPDATE, 0.0, (double)n * T * (last ? 20.0 : 32.0), s);
   if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, last);
   else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, last);
   VGM_LAUNCH_OK();

@@ -206,9 +206,9 @@ __global__ void cg_set_count_kernel(int* n_act, int n) { n_act[0] = n; n_act[1] 
 
 __global__ void cg_count_unconverged_kernel(const int* __restrict__ rows, int n_rows, const int* __restrict__ done,
                                             const int* __restrict__ iters, int* __restrict__ out) {
-  // out[0] = #rows not done, out[1] = max iterations
+  // out[0] += #rows not done, out[1] = max iterations (out is zeroed by the caller)
   int bad = 0, mx = 0;
-  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
     const int s = rows[i];
     bad += done[s] ? 0 : 1;
     mx = max(mx, iters[s]);
@@ -217,14 +217,9 @@ __global__ void cg_count_unconverged_kernel(const int* __restrict__ rows, int n_
     bad += __shfl_xor_sync(0xffffffffu, bad, o);
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
-  __shared__ int sb[32], sm[32];
-  if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = bad; sm[threadIdx.x >> 5] = mx; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int b = 0, m = 0;
-    for (int j = 0; j < (int)(blockDim.x >> 5); ++j) { b += sb[j]; m = max(m, sm[j]); }
-    out[0] = b;
-    out[1] = m;
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicAdd(out, bad);
+    atomicMax(out + 1, mx);
   }
 }
 
@@ -361,7 +356,9 @@ static int compact_and_poll(CgBuf& cb, int& cur, const int*& act, int& n_upper, 
 
 static int report_convergence(CgBuf& cb, PcgWs& w, const int* rows, int n_rows, double tol, int cap,
                               vgm_sweep_info* info, Counters& cnt, cudaStream_t s) {
-  cg_count_unconverged_kernel<<<1, 256, 0, s>>>(rows, n_rows, cb.done, cb.iters, w.host_poll_dev);
+  VGM_CUDA_OK(cudaMemsetAsync(w.host_poll_dev, 0, 2 * sizeof(int), s));
+  cg_count_unconverged_kernel<<<min(148, ceil_div(n_rows, 256)), 256, 0, s>>>(rows, n_rows, cb.done, cb.iters,
+                                                                              w.host_poll_dev);
   VGM_LAUNCH_OK();
   int res[2] = {0, 0};
   VGM_CUDA_OK(cudaMemcpyAsync(res, w.host_poll_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));

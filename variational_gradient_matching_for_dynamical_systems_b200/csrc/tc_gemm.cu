@@ -32,12 +32,17 @@ constexpr int TC_TILE_BYTES = 128 * TC_BK * 2;                 // one 128 x 64 b
 constexpr int TC_TMEM_COLS = 2 * TC_BN;
 constexpr int TC_OUT_TILE_BYTES = 32 * 32 * 4;                 // one 32-row x 32-column FP32 chunk of the output
 constexpr int TC_OUT_STAGING = TC_EPI_WARPS * 2 * TC_OUT_TILE_BYTES;   // two chunks per epilogue warp (TMA store ring)
-template <bool SPLIT>
+constexpr int TC_BRES_KB = 4;                                  // k-blocks of B a CTA can keep resident
+// BRES ("B resident"): a CTA is bound to one column tile, loads the k-blocks of the operator that tile needs ONCE
+// and streams only the A operand; possible when the band leaves <= TC_BRES_KB k-blocks per tile.  It halves the
+// L2 -> SMEM traffic, which is what bounds the streaming variant on the narrow low-precision bands.
+template <bool SPLIT, bool BRES>
 struct TcCfg {
   static constexpr int PARTS = SPLIT ? 2 : 1;                  // (hi, lo) or hi only, for A and for B
-  static constexpr int STAGE_BYTES = 2 * PARTS * TC_TILE_BYTES;
-  static constexpr int STAGES = SPLIT ? 3 : 6;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + TC_OUT_STAGING + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGE_BYTES = (BRES ? 1 : 2) * PARTS * TC_TILE_BYTES;
+  static constexpr int STAGES = BRES ? (SPLIT ? 2 : 6) : (SPLIT ? 3 : 6);
+  static constexpr int RES_BYTES = BRES ? TC_BRES_KB * PARTS * TC_TILE_BYTES : 0;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + RES_BYTES + TC_OUT_STAGING + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -134,34 +139,43 @@ __device__ __forceinline__ void tc_k_range(int ct, int K, int band, int& kb_lo, 
   }
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool BRES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
-  using Cfg = TcCfg<SPLIT>;
+  using Cfg = TcCfg<SPLIT, BRES>;
   constexpr int STAGES = Cfg::STAGES, PARTS = Cfg::PARTS;
   extern __shared__ unsigned char tc_smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  // stage layout: [A0][A1 if split][B0][B1 if split], 16 KB each
-  unsigned char* out_stage = smem + STAGES * Cfg::STAGE_BYTES;   // [EPI_WARPS][2][32 x 128 B], 128B-swizzled rows
+  // stage layout: [A0][A1 if split] ([B0][B1 if split] unless BRES), 16 KB each; BRES keeps [kb][B0][B1] after them
+  unsigned char* b_res = smem + STAGES * Cfg::STAGE_BYTES;
+  unsigned char* out_stage = b_res + Cfg::RES_BYTES;             // [EPI_WARPS][2][32 x 128 B], 128B-swizzled rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + TC_OUT_STAGING);
   uint64_t* full_bar = bars;                                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;                        // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;                    // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;               // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* b_full = bars + 2 * STAGES + 4;                   // BRES: the resident operator tiles have landed
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int row_tiles = (n_rows + TC_BM - 1) / TC_BM;
   const int col_tiles = (a.M + TC_BN - 1) / TC_BN;
   const int n_tiles = row_tiles * col_tiles;
+  // work items of this CTA: u = u_first, u_first + u_step, ... < u_end;  streaming: u = tile index (row-tile major);
+  // BRES: the column tile is fixed (blockIdx.x % col_tiles) and u runs over the row tiles
+  const int u_first = BRES ? (int)blockIdx.x / col_tiles : (int)blockIdx.x;
+  const int u_step = BRES ? (int)gridDim.x / col_tiles : (int)gridDim.x;
+  const int u_end = BRES ? row_tiles : n_tiles;
+  const int ct_fixed = (int)blockIdx.x % col_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(b_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 32 * TC_EPI_WARPS);
@@ -182,8 +196,18 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int rt = tile / col_tiles, ct = tile % col_tiles;
+      if (BRES && u_first < u_end) {                         // the operator tiles of this CTA's column tile, once
+        int kb_lo, kb_hi;
+        tc_k_range(ct_fixed, a.K, a.band, kb_lo, kb_hi);
+        mbar_expect_tx(b_full, (uint32_t)(kb_hi - kb_lo) * PARTS * TC_TILE_BYTES);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          unsigned char* rb = b_res + (kb - kb_lo) * PARTS * TC_TILE_BYTES;
+          tma_load_2d(rb, &maps.b0, b_full, kb * TC_BK, ct_fixed * TC_BN);
+          if (SPLIT) tma_load_2d(rb + TC_TILE_BYTES, &maps.b1, b_full, kb * TC_BK, ct_fixed * TC_BN);
+        }
+      }
+      for (int u = u_first; u < u_end; u += u_step) {
+        const int rt = BRES ? u : u / col_tiles, ct = BRES ? ct_fixed : u % col_tiles;
         int kb_lo, kb_hi;
         tc_k_range(ct, a.K, a.band, kb_lo, kb_hi);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
@@ -192,8 +216,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
           unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
           tma_load_2d(st, &maps.a0, &full_bar[stage], kb * TC_BK, rt * TC_BM);
           if (SPLIT) tma_load_2d(st + TC_TILE_BYTES, &maps.a1, &full_bar[stage], kb * TC_BK, rt * TC_BM);
-          tma_load_2d(st + PARTS * TC_TILE_BYTES, &maps.b0, &full_bar[stage], kb * TC_BK, ct * TC_BN);
-          if (SPLIT) tma_load_2d(st + (PARTS + 1) * TC_TILE_BYTES, &maps.b1, &full_bar[stage], kb * TC_BK, ct * TC_BN);
+          if (!BRES) {
+            tma_load_2d(st + PARTS * TC_TILE_BYTES, &maps.b0, &full_bar[stage], kb * TC_BK, ct * TC_BN);
+            if (SPLIT) tma_load_2d(st + (PARTS + 1) * TC_TILE_BYTES, &maps.b1, &full_bar[stage], kb * TC_BK, ct * TC_BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -204,8 +230,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int ct = tile % col_tiles;
+      if (BRES && u_first < u_end) {
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+      }
+      for (int u = u_first; u < u_end; u += u_step, ++it) {
+        const int ct = BRES ? ct_fixed : u % col_tiles;
         int kb_lo, kb_hi;
         tc_k_range(ct, a.K, a.band, kb_lo, kb_hi);
         const int acc = it & 1;
@@ -218,8 +248,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
           mbar_wait(&full_bar[stage], phase);             // TMA landed this stage
           tc_fence_after();
           unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+          unsigned char* bt = BRES ? b_res + (kb - kb_lo) * PARTS * TC_TILE_BYTES : st + PARTS * TC_TILE_BYTES;
           const uint64_t a0 = make_sw128_desc(st);
-          const uint64_t b0 = make_sw128_desc(st + PARTS * TC_TILE_BYTES);
+          const uint64_t b0 = make_sw128_desc(bt);
           // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
@@ -228,7 +259,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
           }
           if (SPLIT) {
             const uint64_t a1 = make_sw128_desc(st + TC_TILE_BYTES);
-            const uint64_t b1 = make_sw128_desc(st + (PARTS + 1) * TC_TILE_BYTES);
+            const uint64_t b1 = make_sw128_desc(bt + TC_TILE_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
               tc_mma_bf16(tmem_d, a1 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), TC_IDESC, 1u);
@@ -247,8 +278,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
     int it = 0;
     int epi_buf = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int rt = tile / col_tiles, ct = tile % col_tiles;
+    for (int u = u_first; u < u_end; u += u_step, ++it) {
+      const int rt = BRES ? u : u / col_tiles, ct = BRES ? ct_fixed : u % col_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -327,19 +358,38 @@ static int make_bf16_map(CUtensorMap* map, const void* base, int rows, int cols,
   return make_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, TC_BK, box_rows);
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool BRES>
 static int tc_launch(const TcMaps& maps, const TcGemmArgs& args, int n_sm, cudaStream_t s) {
-  using Cfg = TcCfg<SPLIT>;
+  using Cfg = TcCfg<SPLIT, BRES>;
   static bool attr = false;
   if (!attr) {
-    VGM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VGM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<SPLIT, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  const int tiles = ceil_div(args.n_rows, TC_BM) * ceil_div(args.M, TC_BN);
-  const int grid = tiles < n_sm ? tiles : n_sm;
-  tc_gemm_kernel<SPLIT><<<grid, TC_THREADS, Cfg::SMEM, s>>>(maps, args);
+  const int row_tiles = ceil_div(args.n_rows, TC_BM), col_tiles = ceil_div(args.M, TC_BN);
+  int grid;
+  if (BRES) {
+    const int per_col = max(1, min(row_tiles, n_sm / col_tiles));
+    grid = per_col * col_tiles;                              // a multiple of col_tiles: CTA b serves column tile b % col_tiles
+  } else {
+    grid = min(row_tiles * col_tiles, n_sm);
+  }
+  tc_gemm_kernel<SPLIT, BRES><<<grid, TC_THREADS, Cfg::SMEM, s>>>(maps, args);
   VGM_LAUNCH_OK();
   return VGM_OK;
+}
+
+// can every column tile keep its operator k-blocks resident?
+static bool tc_bres_ok(const TcGemmArgs& a, int n_sm) {
+  static const bool off = getenv("VGM_TC_NO_BRES") != nullptr;
+  const int col_tiles = ceil_div(a.M, TC_BN);
+  if (off || a.band <= 0 || col_tiles > n_sm || ceil_div(a.n_rows, TC_BM) < 2 * (n_sm / col_tiles)) return false;
+  for (int ct = 0; ct < col_tiles; ++ct) {
+    const int m0 = ct * TC_BN;
+    const int lo = max(0, m0 - a.band) / TC_BK, hi = ceil_div(min(a.K, m0 + TC_BN + a.band), TC_BK);
+    if (hi - lo > TC_BRES_KB) return false;
+  }
+  return true;
 }
 
 int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
@@ -376,7 +426,9 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
   const double flops = 2.0 * args.n_rows * TC_BN * ksum * (split ? 3.0 : 1.0);
   const double bytes = (double)args.n_rows * args.K * 2.0 * (split ? 2.0 : 1.0) + (double)args.n_rows * args.M * 4.0;
   ProfScope prof(PROF_TCGEMM, flops, bytes, s);
-  return split ? tc_launch<true>(maps, largs, n_sm, s) : tc_launch<false>(maps, largs, n_sm, s);
+  if (tc_bres_ok(largs, n_sm))
+    return split ? tc_launch<true, true>(maps, largs, n_sm, s) : tc_launch<false, true>(maps, largs, n_sm, s);
+  return split ? tc_launch<true, false>(maps, largs, n_sm, s) : tc_launch<false, false>(maps, largs, n_sm, s);
 }
 
 __global__ void f64_to_bf16_kernel(const double* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {

@@ -4,7 +4,8 @@
 
 namespace vgm {
 
-enum { PROF_DGEMM = 0, PROF_TCGEMM = 1, PROF_VEC = 2, PROF_ASSEMBLE = 3, PROF_FAMILIES = 4 };
+enum { PROF_DGEMM = 0, PROF_TCGEMM = 1, PROF_VEC = 2, PROF_ASSEMBLE = 3, PROF_IR_UPDATE = 4, PROF_IR_DIR = 5,
+       PROF_FAMILIES = 6 };
 
 // Records an event pair around the launches issued during its lifetime when profiling is enabled
 // (vgm_profile_enable); a no-op otherwise.  `flops` / `bytes` are the algorithmic work of the launches.
