@@ -207,7 +207,8 @@ int vgm_tc_gemm_bf16(const void* A0, const void* A1, int n_rows, int lda, const 
 
 typedef struct {
   double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)                     */
-  int max_iter;      /* FP64 PCG: iteration cap (default 4 T); mixed precision: cap on outer corrections (default 30) */
+  int max_iter;      /* FP64 PCG: iteration cap (default 4 T).  The mixed-precision solver allows 12 corrections; systems
+                        that stagnate (too ill-conditioned for FP32 / bf16-split corrections) are finished by FP64 PCG */
   int check_every;   /* FP64 PCG: host polls the device-side active count every this many iterations         */
   int inner_iters;   /* mixed precision: FP32 PCG steps per correction (default 10)                           */
   int optimistic_passes; /* mixed precision: corrections enqueued before the first convergence poll (default 4;

@@ -199,6 +199,28 @@ def test_mixed_precision_solver_matches_fp64_pcg_and_oracle(pkg):
     assert relerr(res["mixed"][0], res["pcg"][0]) < 1e-10
 
 
+@pytest.mark.parametrize("T,ell", [(1100, 0.0625), (1000, 0.1), (250, 0.0625)])
+def test_mixed_solver_other_shapes_vs_oracle(pkg, T, ell):
+    """Shapes off the benchmark's beaten path: T > 1024 (vector kernels keep the row in shared memory instead of
+    registers), T not a multiple of 8, and a longer length scale (l = 2 dt: wider bands, cond(A) beyond the reach of
+    bf16-split corrections, so the refinement stagnates and FP64 PCG finishes the systems)."""
+    p, _lib, engine = pkg
+    K = 12
+    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=31)
+    rng = np.random.default_rng(32)
+    X0 = Xtrue.copy()
+    X0[:, 1::2] += 0.5 * rng.standard_normal((T, K // 2))
+    D, A, *_ = vo.kernel_function(t, t, "rbf", [ell, 1.0])
+    hidden = list(range(1, K, 2))
+    Xref = vo.lorenz96_state_sweep(X0, 8.0, D, hidden)
+    eng = engine.VGMEngine(p.OdeModel.lorenz96(K), D, A, hidden=hidden, solver="mixed")
+    eng.set_states(X0)
+    eng.theta_step()
+    info = eng.state_sweep()
+    assert relerr(eng.get_states(), Xref) < TOL, (info, eng.ops.band_D, eng.ops.band_M, eng.ops.band_M_lp, eng.ops.band_G)
+    assert info["unconverged"] == 0
+
+
 def test_all_hidden_chain_with_the_single_cta_solver(pkg):
     """Lorenz96 K=12, T=160 with EVERY state hidden: 12 dependency levels of one system each (the reference's
     sequential order); each level is one launch of the banded-Cholesky + refinement kernel (small_solve.cu)."""

@@ -354,8 +354,9 @@ static int compact_and_poll(CgBuf& cb, int& cur, const int*& act, int& n_upper, 
   return VGM_OK;
 }
 
+// `final` = false: a non-converged result is only reported through the return code (the caller has a fallback)
 static int report_convergence(CgBuf& cb, PcgWs& w, const int* rows, int n_rows, double tol, int cap,
-                              vgm_sweep_info* info, Counters& cnt, cudaStream_t s) {
+                              vgm_sweep_info* info, Counters& cnt, cudaStream_t s, bool final = true) {
   VGM_CUDA_OK(cudaMemsetAsync(w.host_poll_dev, 0, 2 * sizeof(int), s));
   cg_count_unconverged_kernel<<<min(148, ceil_div(n_rows, 256)), 256, 0, s>>>(rows, n_rows, cb.done, cb.iters,
                                                                               w.host_poll_dev);
@@ -366,10 +367,10 @@ static int report_convergence(CgBuf& cb, PcgWs& w, const int* rows, int n_rows, 
   cnt.launches += 1;
   if (info) {
     info->iterations = max(info->iterations, res[1]);
-    info->unconverged += res[0];
+    if (final) info->unconverged += res[0];
   }
   if (res[0] > 0) {
-    set_error("solver: %d of %d systems did not reach tol=%g within %d iterations", res[0], n_rows, tol, cap);
+    if (final) set_error("solver: %d of %d systems did not reach tol=%g within %d iterations", res[0], n_rows, tol, cap);
     return VGM_ENOTCONV;
   }
   return VGM_OK;
@@ -468,6 +469,7 @@ static IrBuf ir_view(const IrBuf& b, int row0, int ld) {
   return v;
 }
 
+constexpr int IR_MAX_OUTER = 12;
 constexpr int IR_CHUNK_MIN_ROWS = 4096;   // a chunk is at least this many rows; smaller levels run as one chunk
 static int ir_chunk_target() {
   static int n = 0;
@@ -483,7 +485,9 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
                     const int* slot_state, const int* slot_has_self, const int* rows, int n_rows, int T, int ld,
                     const vgm_solver_opts* opts, PcgWs& w, vgm_sweep_info* info, Counters& cnt, cudaStream_t s) {
   const double tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
-  const int max_outer = (opts && opts->max_iter > 0) ? opts->max_iter : 30;
+  // a correction normally gains 3-4 digits; a system that needs more than IR_MAX_OUTER of them is too ill-conditioned
+  // for FP32 / bf16-split corrections (cond(A) 2^-16 >~ 1) and is handed to FP64 PCG by the caller
+  const int max_outer = IR_MAX_OUTER;
   const int inner = (opts && opts->inner_iters > 0) ? opts->inner_iters : 10;
   // corrections enqueued back to back before the host looks at a convergence count for the first time: the
   // kernels read the exact active count on the device, so a pass over already converged rows costs nothing
@@ -606,7 +610,7 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
     VGM_CUDA_OK(cudaEventRecord(as.join[c], as.side[c]));
     VGM_CUDA_OK(cudaStreamWaitEvent(s, as.join[c], 0));
   }
-  return report_convergence(cb, w, rows, n_rows, tol, max_outer * inner, info, cnt, s);
+  return report_convergence(cb, w, rows, n_rows, tol, max_outer * inner, info, cnt, s, /*final=*/false);
 }
 
 static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu, const double* Lambda,
@@ -656,10 +660,17 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
     // fall through to the batched solver (x was left untouched for the systems that did not converge)
   }
   // mixed precision needs the bf16 operators and tiles that the TMA boxes (128 x 64) fit into
-  if (ruu_const && ops->G_bf16 && ops->M_bf16x2 && T >= 128)
-    return ir_solve(ops, Lambda, rhs, X, slot_state, slot_has_self, rows, n_rows, T, ld, opts, w, info, cnt, s);
+  bool after_mixed = false;
+  if (ruu_const && ops->G_bf16 && ops->M_bf16x2 && T >= 128) {
+    int r = ir_solve(ops, Lambda, rhs, X, slot_state, slot_has_self, rows, n_rows, T, ld, opts, w, info, cnt, s);
+    if (r != VGM_ENOTCONV) return r;
+    // stagnated rows: finish them with FP64 preconditioned CG, warm-started from the refined x (rows that did
+    // converge are recognised by their residual in cg_init_kernel and cost one operator application)
+    if (g_debug) fprintf(stderr, "[vgm] mixed-precision refinement stagnated on some systems: FP64 PCG takes over\n");
+    after_mixed = true;
+  }
   const double tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
-  const int max_iter = (opts && opts->max_iter > 0) ? opts->max_iter : 4 * T;
+  const int max_iter = (opts && opts->max_iter > 0 && !after_mixed) ? opts->max_iter : 4 * T;
   const int check_every = (opts && opts->check_every > 0) ? opts->check_every : 8;
   const int precond = (ruu_const && ops->G) ? 1 : 0;
   const double tol2 = tol * tol;
