@@ -418,6 +418,37 @@ def test_multi_parameter_models_vs_patched_reference_golden(pkg, fname):
         assert relerr(eng.get_states(), g["states"][it]) < TOL, (it, eng.last_info)
 
 
+def test_trajectory_batch_pools_the_parameter_statistics(pkg):
+    """Config C4 in miniature: a batch of independent Protein-Transduction trajectories (K_m -> 0.3, the closed-form
+    variant of the golden file) shares one theta.  The statistics sum_n sum_k B^T B, B^T (D x - b) are pooled over
+    the trajectories and every trajectory's hidden states are then swept with the pooled theta."""
+    import sympy as sym
+    p, _lib, engine = pkg
+    g = load("protein_transduction_T99.npz")
+    lines, params, names = [str(s) for s in g["lines"]], [str(s) for s in g["params"]], [str(s) for s in g["names"]]
+    sc = [[int(v) for v in str(c).split(",") if v != ""] for c in g["couplings"]]
+    observed = [str(s) for s in g["observed"]]
+    hidden1 = [u for u in range(len(names)) if names[u] not in observed]
+    lin = vo.Linearisation(vo.parse_ode_lines(lines), sym.symbols(names), sym.symbols(params), couplings=sc)
+    N, K1, T = 6, len(names), g["X0"].shape[0]
+    rng = np.random.default_rng(41)
+    Xn = [g["X0"] * (1.0 + 0.05 * rng.standard_normal((1, K1))) for _ in range(N)]
+    m, S = 0.0, 0.0
+    for X in Xn:
+        _, mn, Sn, _ = vo.theta_step(X, lin, g["D"])
+        m, S = m + mn, S + Sn
+    theta_ref = np.linalg.solve(S, m)
+    Xref = np.concatenate([vo.state_sweep(X, theta_ref, lin, g["D"], hidden1)[0] for X in Xn], axis=1)
+    model = p.OdeModel(lines, names, params, n_copies=N)
+    hidden = [n * K1 + u for n in range(N) for u in hidden1]
+    eng = engine.VGMEngine(model, g["D"], g["A"], hidden=hidden, couplings=sc, theta_mode="proxy")
+    eng.set_states(np.concatenate(Xn, axis=1))
+    th = eng.theta_step().cpu().numpy()
+    assert relerr(th, theta_ref) < TOL
+    eng.state_sweep()
+    assert relerr(eng.get_states(), Xref) < TOL, eng.last_info
+
+
 def test_lorenz96_K1000_T1000_vs_oracle(pkg):
     """Config C3 (Lorenz96 K=1000, T=1000): full iteration against the NumPy restatement."""
     p, _lib, engine = pkg
