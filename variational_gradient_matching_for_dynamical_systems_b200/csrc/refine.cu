@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, const int* 
   IR_ROW_LOOP(i, T) {
     const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
     const float4 sv = ld_bf4(b.s16 + o + i);
-    const float4 r = ld_f4(b.r32 + o + i);
+    const float4 rs = ld_bf4(b.rsb + o + i);               // r.z = (s o r).acc, with the rounded s o r the GEMM saw
     const float4 z = make_float4(sv.x * acc.x, sv.y * acc.y, sv.z * acc.z, sv.w * acc.w);
     if (REG) zreg = z; else *reinterpret_cast<float4*>(ir_sm + i) = z;
-    part += (double)r.x * z.x + (double)r.y * z.y + (double)r.z * z.z + (double)r.w * z.w;
+    part += (double)rs.x * acc.x + (double)rs.y * acc.y + (double)rs.z * acc.z + (double)rs.w * acc.w;
   }
   float4 hreg = zreg, lreg = zreg;
   if (REG && !first) {
@@ -172,8 +172,10 @@ __device__ __forceinline__ float4 axpy4(float s, float4 a, float4 b) {
   return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
 }
 __device__ __forceinline__ float4 bfr4(float4 a) { return make_float4(bf_round(a.x), bf_round(a.y), bf_round(a.z), bf_round(a.w)); }
-__device__ __forceinline__ double dot4(float4 a, float4 b) {
-  return (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+// per-lane partial dot products stay in FP32 (a lane adds at most 32 products; FP32 -> FP64 conversions run at a
+// fraction of the FP32 rate and showed up as the busiest pipe of these kernels); rows are reduced in FP64
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
 __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const int* __restrict__ n_dev, int n, int T,
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const 
   if (j >= nn) return;
   const size_t o = (size_t)j * ld;
   f8 z[IR_WG], pp[IR_WG];
-  double part = 0.0;
+  float part = 0.f;
 #pragma unroll
   for (int g = 0; g < IR_WG; ++g) {
     const int i = 8 * (lane + 32 * g);
@@ -192,16 +194,16 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const 
     if (i < T) {                                              // T % 8 == 0: whole groups only
       const float4 a0 = ld_f4(b.acc32 + o + i), a1 = ld_f4(b.acc32 + o + i + 4);
       const f8 sv = ld_bf8(b.s16 + o + i);
-      const float4 r0 = ld_f4(b.r32 + o + i), r1 = ld_f4(b.r32 + o + i + 4);
+      const f8 rs = ld_bf8(b.rsb + o + i);                   // r.z = (s o r).acc, with the rounded s o r the GEMM saw
       if (!first) {
         const f8 h = ld_bf8(b.p_hi + o + i), l = ld_bf8(b.p_lo + o + i);
         pp[g].a = add4(h.a, l.a); pp[g].b = add4(h.b, l.b);
       }
       z[g].a = mul4(sv.a, a0); z[g].b = mul4(sv.b, a1);
-      part += dot4(r0, z[g].a) + dot4(r1, z[g].b);
+      part += dot4(rs.a, a0) + dot4(rs.b, a1);
     }
   }
-  const double rz_new = warp_sum(part);
+  const double rz_new = warp_sum((double)part);
   const double rz_old = first ? 0.0 : b.rz[j];
   const float beta = (first || !(rz_old > 0.0)) ? 0.f : (float)(rz_new / rz_old);
 #pragma unroll
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
   const int j = blockIdx.x;
   if (n_dev && j >= *n_dev) return;
   const size_t o = (size_t)j * ld;
-  double part = 0.0;
+  float part = 0.f;
   float4 preg = make_float4(0.f, 0.f, 0.f, 0.f), qreg = preg;
   IR_ROW_LOOP(i, T) {
     const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
       *reinterpret_cast<float4*>(sp + i) = p;
       *reinterpret_cast<float4*>(sq + i) = q;
     }
-    part += (double)p.x * q.x + (double)p.y * q.y + (double)p.z * q.z + (double)p.w * q.w;
+    part += fmaf(p.x, q.x, fmaf(p.y, q.y, fmaf(p.z, q.z, p.w * q.w)));
   }
   // REG: issue the loads of the second phase before the row-wide reduction so their latency hides behind it
   float4 dreg = preg, rreg = preg, sreg = preg;
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
       if (!last) { rreg = ld_f4(b.r32 + o + i); sreg = ld_bf4(b.s16 + o + i); }
     }
   }
-  const double pq = block_sum(part, red);
+  const double pq = block_sum((double)part, red);
   const float alpha = (pq > 0.0) ? (float)(b.rz[j] / pq) : 0.f;
   IR_ROW_LOOP(i, T) {
     const float4 p = REG ? preg : *reinterpret_cast<const float4*>(sp + i);
@@ -297,8 +299,8 @@ int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const d
 
 int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
-  // reads acc32 4, s16 2, r32 4, (p_hi, p_lo 4); writes p_hi, p_lo 4
-  ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * (first ? 14.0 : 18.0), s);
+  // reads acc32 4, s16 2, rsb 2, (p_hi, p_lo 4); writes p_hi, p_lo 4
+  ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * (first ? 12.0 : 16.0), s);
   if (T <= 8 * 32 * IR_WG && (T % 8) == 0) ir_dir_warp_kernel<<<ceil_div(n, IR_THREADS / 32), IR_THREADS, 0, s>>>(b, n_dev, n, T, ld, first);
   else if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, first);
   else ir_dir_kernel<false><<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, first);

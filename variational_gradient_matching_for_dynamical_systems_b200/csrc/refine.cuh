@@ -20,7 +20,7 @@ void ir_carve(char*& p, int n, int ld, IrBuf& b);
 // `n` is a host upper bound of the row count; `n_dev` (optional) the exact device-side count.
 int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
                   const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s);
-// z = s o acc32; rz' = r.z; beta = first ? 0 : rz'/rz; p = z + beta p  ->  (p_hi, p_lo)
+// z = s o acc32; rz' = (s o r).acc32 (the bf16 s o r the GEMM consumed); beta = first ? 0 : rz'/rz; p = z + beta p -> (p_hi, p_lo)
 int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s);
 // q = acc32 + lam o p; alpha = rz / p.q; d += alpha p; r -= alpha q; rsb = bf16(s o r)
 int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, cudaStream_t s);

