@@ -58,6 +58,7 @@ ProfScope::ProfScope(int fam, double flops, double bytes, cudaStream_t s) : fami
   f.launches += 1;
   active = true;
 }
+bool profile_enabled() { return g_prof_on; }
 ProfScope::~ProfScope() {
   if (active) cudaEventRecord(stop, stream);
 }

@@ -470,6 +470,24 @@ static IrBuf ir_view(const IrBuf& b, int row0, int ld) {
 }
 
 constexpr int IR_MAX_OUTER = 12;
+// A correction over a small active set (straggler passes, the wrap-around level, small per-GPU blocks) is ~45
+// launch-bound kernels; it is captured once into a CUDA graph (kernels read the exact row count on the device, so
+// the same graph serves every pass over at most IR_GRAPH_MAX_ROWS rows) and replayed.
+constexpr int IR_GRAPH_MAX_ROWS = 1024;
+struct IrGraphKey {
+  const void *r32, *act, *n_act, *G, *M, *X, *Lambda, *R, *P, *rr, *slot_state;
+  int n, T, ld, inner, band_G, band_M;
+  double shift, c;
+  bool operator==(const IrGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+};
+struct IrGraphEntry {
+  IrGraphKey key;
+  cudaGraphExec_t exec;
+};
+constexpr int IR_GRAPH_CACHE = 16;
+static IrGraphEntry g_ir_graphs[IR_GRAPH_CACHE];
+static int g_ir_graph_count = 0, g_ir_graph_next = 0;
+static const bool g_no_graph = getenv("VGM_NO_GRAPH") != nullptr;
 constexpr int IR_CHUNK_MIN_ROWS = 4096;   // a chunk is at least this many rows; smaller levels run as one chunk
 static int ir_chunk_target() {
   static int n = 0;
@@ -579,30 +597,62 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
         if (k.n_upper == 0 || outer == max_outer) { k.finished = true; continue; }
       }
       any = true;
-      const int n = k.n_upper;                              // host upper bound; k.n_act is exact
-      VGM_TRY(ir_inner_init(k.ir, cb.R, Lambda, cb.rr, k.act, n, k.n_act, T, ld, ops->G_shift, ops->precond_c, k.st));
-      TcGemmArgs tg;
-      memset(&tg, 0, sizeof(tg));
-      tg.n_rows = n; tg.n_rows_dev = k.n_act; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = k.ir.acc32; tg.ldo = ld;
-      TcGemmArgs tp = tg;                                   // z' = (s o r) G^T
-      tp.A0 = k.ir.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
-      TcGemmArgs to = tg;                                   // q' = p M^T (bf16 split)
-      to.A0 = k.ir.p_hi; to.A1 = k.ir.p_lo; to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
-      VGM_TRY(tc_gemm(tp, k.st));
-      VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 1, k.st));
-      cnt.launches += 3; cnt.gemm += 1;
-      for (int it = 0; it < inner; ++it) {
-        const int last = (it == inner - 1) ? 1 : 0;
-        VGM_TRY(tc_gemm(to, k.st));
-        VGM_TRY(ir_update(k.ir, n, k.n_act, T, ld, last, k.st));
-        cnt.launches += 2; cnt.gemm += 1;
-        if (last) break;
-        VGM_TRY(tc_gemm(tp, k.st));
-        VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 0, k.st));
-        cnt.launches += 2; cnt.gemm += 1;
+      // n: host upper bound of the rows (k.n_act is exact); st: the stream to enqueue on / capture from
+      auto enqueue_correction = [&](int n, cudaStream_t st) -> int {
+        VGM_TRY(ir_inner_init(k.ir, cb.R, Lambda, cb.rr, k.act, n, k.n_act, T, ld, ops->G_shift, ops->precond_c, st));
+        TcGemmArgs tg;
+        memset(&tg, 0, sizeof(tg));
+        tg.n_rows = n; tg.n_rows_dev = k.n_act; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = k.ir.acc32; tg.ldo = ld;
+        TcGemmArgs tp = tg;                                 // z' = (s o r) G^T
+        tp.A0 = k.ir.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
+        TcGemmArgs to = tg;                                 // q' = p M^T (bf16 split)
+        to.A0 = k.ir.p_hi; to.A1 = k.ir.p_lo; to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
+        VGM_TRY(tc_gemm(tp, st));
+        VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 1, st));
+        for (int it = 0; it < inner; ++it) {
+          const int last = (it == inner - 1) ? 1 : 0;
+          VGM_TRY(tc_gemm(to, st));
+          VGM_TRY(ir_update(k.ir, n, k.n_act, T, ld, last, st));
+          if (last) break;
+          VGM_TRY(tc_gemm(tp, st));
+          VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 0, st));
+        }
+        return ir_finish(k.ir, cb.P, X, slot_state, k.act, n, k.n_act, T, ld, st);
+      };
+      cnt.launches += 4 * inner + 2; cnt.gemm += 2 * inner;
+      const bool use_graph = !g_no_graph && !profile_enabled() && k.n_upper <= IR_GRAPH_MAX_ROWS;
+      if (!use_graph) {
+        VGM_TRY(enqueue_correction(k.n_upper, k.st));
+        continue;
       }
-      VGM_TRY(ir_finish(k.ir, cb.P, X, slot_state, k.act, n, k.n_act, T, ld, k.st));
-      cnt.launches += 1;
+      IrGraphKey key;
+      memset(&key, 0, sizeof(key));
+      key.r32 = k.ir.r32; key.act = k.act; key.n_act = k.n_act; key.G = ops->G_bf16; key.M = ops->M_bf16x2; key.X = X;
+      key.Lambda = Lambda; key.R = cb.R; key.P = cb.P; key.rr = cb.rr; key.slot_state = slot_state;
+      key.n = min(k.n_rows, IR_GRAPH_MAX_ROWS); key.T = T; key.ld = ld; key.inner = inner;
+      key.band_G = ops->band_G; key.band_M = ops->band_M_lp; key.shift = ops->G_shift; key.c = ops->precond_c;
+      cudaGraphExec_t exec = nullptr;
+      for (int i = 0; i < g_ir_graph_count; ++i)
+        if (g_ir_graphs[i].key == key) exec = g_ir_graphs[i].exec;
+      if (!exec) {
+        cudaGraph_t graph = nullptr;
+        // the caller's stream may be the legacy default stream, which cannot be captured: record the sequence on
+        // an internal stream (nothing executes during capture) and replay it wherever the solve runs
+        cudaStream_t cap = as.side[IR_MAX_CHUNKS - 1];
+        VGM_CUDA_OK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
+        const int rc_cap = enqueue_correction(key.n, cap);
+        const cudaError_t e_cap = cudaStreamEndCapture(cap, &graph);
+        if (rc_cap != VGM_OK) { if (graph) cudaGraphDestroy(graph); return rc_cap; }
+        VGM_CUDA_OK(e_cap);
+        VGM_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+        VGM_CUDA_OK(cudaGraphDestroy(graph));
+        IrGraphEntry& slot_e = g_ir_graphs[g_ir_graph_next];
+        if (g_ir_graph_count == IR_GRAPH_CACHE && slot_e.exec) cudaGraphExecDestroy(slot_e.exec);
+        slot_e.key = key; slot_e.exec = exec;
+        g_ir_graph_next = (g_ir_graph_next + 1) % IR_GRAPH_CACHE;
+        g_ir_graph_count = min(g_ir_graph_count + 1, IR_GRAPH_CACHE);
+      }
+      VGM_CUDA_OK(cudaGraphLaunch(exec, k.st));
     }
     if (!any) break;
   }

@@ -18,4 +18,6 @@ struct ProfScope {
   bool active;
 };
 
+bool profile_enabled();
+
 }  // namespace vgm
