@@ -19,7 +19,7 @@ size_t ir_ws_bytes(int n, int ld) {
   const size_t f32 = align_up((size_t)n * ld * sizeof(float), 256);
   const size_t b16 = align_up((size_t)n * ld * sizeof(__nv_bfloat16), 256);
   const size_t vec = align_up((size_t)n * sizeof(double), 256);
-  return 4 * f32 + 4 * b16 + 2 * vec;
+  return 4 * f32 + 6 * b16 + 2 * vec;
 }
 
 void ir_carve(char*& p, int n, int ld, IrBuf& b) {
@@ -32,6 +32,8 @@ void ir_carve(char*& p, int n, int ld, IrBuf& b) {
   b.lam32 = (float*)p; p += f32;
   b.p_hi = (__nv_bfloat16*)p; p += b16;
   b.p_lo = (__nv_bfloat16*)p; p += b16;
+  b.q_hi = (__nv_bfloat16*)p; p += b16;
+  b.q_lo = (__nv_bfloat16*)p; p += b16;
   b.rsb = (__nv_bfloat16*)p; p += b16;
   b.s16 = (__nv_bfloat16*)p; p += b16;
   b.sigma = (double*)p; p += vec;
@@ -135,8 +137,8 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, const int* 
       p.x += beta * (h.x + l.x); p.y += beta * (h.y + l.y); p.z += beta * (h.z + l.z); p.w += beta * (h.w + l.w);
     }
     const float4 hi = make_float4(bf_round(p.x), bf_round(p.y), bf_round(p.z), bf_round(p.w));
-    st_bf4(b.p_hi + o + i, hi);
-    st_bf4(b.p_lo + o + i, make_float4(p.x - hi.x, p.y - hi.y, p.z - hi.z, p.w - hi.w));
+    st_bf4(b.q_hi + o + i, hi);
+    st_bf4(b.q_lo + o + i, make_float4(p.x - hi.x, p.y - hi.y, p.z - hi.z, p.w - hi.w));
   }
   if (threadIdx.x == 0) b.rz[j] = rz_new;
 }
@@ -212,8 +214,8 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const 
     if (i < T) {
       const float4 p0 = axpy4(beta, pp[g].a, z[g].a), p1 = axpy4(beta, pp[g].b, z[g].b);
       const float4 h0 = bfr4(p0), h1 = bfr4(p1);
-      st_bf8(b.p_hi + o + i, h0, h1);
-      st_bf8(b.p_lo + o + i, sub4(p0, h0), sub4(p1, h1));
+      st_bf8(b.q_hi + o + i, h0, h1);
+      st_bf8(b.q_lo + o + i, sub4(p0, h0), sub4(p1, h1));
     }
   }
   if (lane == 0) b.rz[j] = rz_new;

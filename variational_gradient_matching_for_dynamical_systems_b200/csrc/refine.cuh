@@ -9,6 +9,8 @@ namespace vgm {
 struct IrBuf {
   float *r32, *d32, *acc32, *lam32;       // [n][ld] residual, correction, GEMM output (q' or z'), Lambda
   __nv_bfloat16 *p_hi, *p_lo;             // [n][ld] search direction p = hi + lo (the tensor-core A operand)
+  __nv_bfloat16 *q_hi, *q_lo;             // [n][ld] where ir_dir writes the NEXT direction (the caller swaps p <-> q):
+                                          // reading and rewriting the same bf16 lines in one kernel cost it 12 %
   __nv_bfloat16 *rsb, *s16;               // [n][ld] bf16(s o r) (A operand of the preconditioner GEMM), scaling s
   double *sigma, *rz;                     // [n] residual norm each row was scaled by; r.z
 };

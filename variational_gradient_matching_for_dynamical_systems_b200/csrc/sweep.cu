@@ -15,6 +15,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <utility>
+
 #include "vgm_common.cuh"
 #include "vgm_profile.cuh"
 #include "tc_gemm.cuh"
@@ -464,7 +466,7 @@ static IrBuf ir_view(const IrBuf& b, int row0, int ld) {
   IrBuf v = b;
   const size_t o = (size_t)row0 * ld;
   v.r32 += o; v.d32 += o; v.acc32 += o; v.lam32 += o;
-  v.p_hi += o; v.p_lo += o; v.rsb += o; v.s16 += o;
+  v.p_hi += o; v.p_lo += o; v.q_hi += o; v.q_lo += o; v.rsb += o; v.s16 += o;
   v.sigma += row0; v.rz += row0;
   return v;
 }
@@ -599,25 +601,30 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
       any = true;
       // n: host upper bound of the rows (k.n_act is exact); st: the stream to enqueue on / capture from
       auto enqueue_correction = [&](int n, cudaStream_t st) -> int {
-        VGM_TRY(ir_inner_init(k.ir, cb.R, Lambda, cb.rr, k.act, n, k.n_act, T, ld, ops->G_shift, ops->precond_c, st));
+        IrBuf ib = k.ir;                                    // ir_dir reads p and writes q: swap after every call
+        auto swap_pq = [&]() { std::swap(ib.p_hi, ib.q_hi); std::swap(ib.p_lo, ib.q_lo); };
+        VGM_TRY(ir_inner_init(ib, cb.R, Lambda, cb.rr, k.act, n, k.n_act, T, ld, ops->G_shift, ops->precond_c, st));
         TcGemmArgs tg;
         memset(&tg, 0, sizeof(tg));
-        tg.n_rows = n; tg.n_rows_dev = k.n_act; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = k.ir.acc32; tg.ldo = ld;
+        tg.n_rows = n; tg.n_rows_dev = k.n_act; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = ib.acc32; tg.ldo = ld;
         TcGemmArgs tp = tg;                                 // z' = (s o r) G^T
-        tp.A0 = k.ir.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
+        tp.A0 = ib.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
         TcGemmArgs to = tg;                                 // q' = p M^T (bf16 split)
-        to.A0 = k.ir.p_hi; to.A1 = k.ir.p_lo; to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
+        to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
         VGM_TRY(tc_gemm(tp, st));
-        VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 1, st));
+        VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 1, st));
+        swap_pq();
         for (int it = 0; it < inner; ++it) {
           const int last = (it == inner - 1) ? 1 : 0;
+          to.A0 = ib.p_hi; to.A1 = ib.p_lo;
           VGM_TRY(tc_gemm(to, st));
-          VGM_TRY(ir_update(k.ir, n, k.n_act, T, ld, last, st));
+          VGM_TRY(ir_update(ib, n, k.n_act, T, ld, last, st));
           if (last) break;
           VGM_TRY(tc_gemm(tp, st));
-          VGM_TRY(ir_dir(k.ir, n, k.n_act, T, ld, 0, st));
+          VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 0, st));
+          swap_pq();
         }
-        return ir_finish(k.ir, cb.P, X, slot_state, k.act, n, k.n_act, T, ld, st);
+        return ir_finish(ib, cb.P, X, slot_state, k.act, n, k.n_act, T, ld, st);
       };
       cnt.launches += 4 * inner + 2; cnt.gemm += 2 * inner;
       const bool use_graph = !g_no_graph && !profile_enabled() && k.n_upper <= IR_GRAPH_MAX_ROWS;
