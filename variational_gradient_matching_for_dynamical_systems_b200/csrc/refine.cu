@@ -82,21 +82,30 @@ ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __rest
   const double sig = sqrt(rr[slot]);
   const double inv = sig > 0.0 ? 1.0 / sig : 0.0;
   const size_t oj = (size_t)j * ld, os = (size_t)slot * ld;
+  // same active list as in the previous correction: row j still belongs to the same system, lam32 / s16 are valid
+  const bool remap = !n_dev || n_dev[2];
   IR_ROW_LOOP(i, T) {
     float4 r, lam, sv;
     float* rp = &r.x; float* lp = &lam.x; float* sp = &sv.x;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const bool ok = i + e < T;
-      const double L = ok ? Lambda[os + i + e] : 0.0;
       rp[e] = ok ? (float)(R[os + i + e] * inv) : 0.f;
-      lp[e] = (float)L;
-      sp[e] = ok ? ((c > 0.0) ? bf_round((float)sqrt((shift + c) / (L + c))) : 1.f) : 0.f;
+    }
+    if (remap) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = i + e < T;
+        const double L = ok ? Lambda[os + i + e] : 0.0;
+        lp[e] = (float)L;
+        sp[e] = ok ? ((c > 0.0) ? bf_round((float)sqrt((shift + c) / (L + c))) : 1.f) : 0.f;
+      }
+      *reinterpret_cast<float4*>(b.lam32 + oj + i) = lam;
+      st_bf4(b.s16 + oj + i, sv);
+    } else {
+      sv = ld_bf4(b.s16 + oj + i);
     }
     *reinterpret_cast<float4*>(b.r32 + oj + i) = r;
-    *reinterpret_cast<float4*>(b.lam32 + oj + i) = lam;
-    *reinterpret_cast<float4*>(b.d32 + oj + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    st_bf4(b.s16 + oj + i, sv);
     st_bf4(b.rsb + oj + i, make_float4(sv.x * r.x, sv.y * r.y, sv.z * r.z, sv.w * r.w));
   }
   if (threadIdx.x == 0) b.sigma[j] = sig;
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const 
 
 template <bool REG>
 __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const int* __restrict__ n_dev, int T, int ld,
-                                                               int last) {
+                                                               int last, int first) {
   extern __shared__ float ir_sm[];       // p and q of this row (!REG)
   __shared__ double red[40];
   float* sp = ir_sm;
@@ -247,11 +256,11 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
     part += fmaf(p.x, q.x, fmaf(p.y, q.y, fmaf(p.z, q.z, p.w * q.w)));
   }
   // REG: issue the loads of the second phase before the row-wide reduction so their latency hides behind it
-  float4 dreg = preg, rreg = preg, sreg = preg;
+  float4 dreg = make_float4(0.f, 0.f, 0.f, 0.f), rreg = preg, sreg = preg;
   if (REG) {
     const int i = 4 * threadIdx.x;
     if (i < T) {
-      dreg = ld_f4(b.d32 + o + i);
+      if (!first) dreg = ld_f4(b.d32 + o + i);             // first step of a correction: d = alpha p
       if (!last) { rreg = ld_f4(b.r32 + o + i); sreg = ld_bf4(b.s16 + o + i); }
     }
   }
@@ -260,7 +269,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
   IR_ROW_LOOP(i, T) {
     const float4 p = REG ? preg : *reinterpret_cast<const float4*>(sp + i);
     const float4 q = REG ? qreg : *reinterpret_cast<const float4*>(sq + i);
-    float4 d = REG ? dreg : ld_f4(b.d32 + o + i);
+    float4 d = REG ? dreg : (first ? make_float4(0.f, 0.f, 0.f, 0.f) : ld_f4(b.d32 + o + i));
     d.x = fmaf(alpha, p.x, d.x); d.y = fmaf(alpha, p.y, d.y); d.z = fmaf(alpha, p.z, d.z); d.w = fmaf(alpha, p.w, d.w);
     *reinterpret_cast<float4*>(b.d32 + o + i) = d;
     if (!last) {
@@ -293,7 +302,7 @@ ir_finish_kernel(IrBuf b, double* __restrict__ P, double* __restrict__ X, const 
 int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
                   const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
-  ProfScope prof(PROF_VEC, 0.0, (double)n * T * (16.0 + 16.0), s);
+  ProfScope prof(PROF_VEC, 0.0, (double)n * T * 16.0, s);   // R in, r32 + rsb out, s16 in (the common case: list unchanged)
   ir_inner_init_kernel<<<n, IR_THREADS, 0, s>>>(b, R, Lambda, rr, act, n_dev, T, ld, shift, c);
   VGM_LAUNCH_OK();
   return VGM_OK;
@@ -310,12 +319,12 @@ int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cu
   return VGM_OK;
 }
 
-int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, cudaStream_t s) {
+int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4, s16 2); writes d32 4, (r32 4, rsb 2)
-  ProfScope prof(PROF_IR_UPDATE, 0.0, (double)n * T * (last ? 20.0 : 32.0), s);
-  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, last);
-  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, last);
+  ProfScope prof(PROF_IR_UPDATE, 0.0, (double)n * T * ((last ? 20.0 : 32.0) - (first ? 4.0 : 0.0)), s);
+  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, last, first);
+  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, last, first);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }

@@ -18,14 +18,16 @@ struct IrBuf {
 size_t ir_ws_bytes(int n, int ld);
 void ir_carve(char*& p, int n, int ld, IrBuf& b);
 
-// r32 = R[slot]/sigma, lam32 = Lambda[slot], s = sqrt((shift + c)/(Lambda + c)) (1 if c <= 0), rsb = bf16(s r), d = 0
+// r32 = R[slot]/sigma, rsb = bf16(s r); lam32 = Lambda[slot] and s = sqrt((shift + c)/(Lambda + c)) (1 if c <= 0) are
+// only rewritten when the active list changed since the previous correction (n_dev[2], set by the compaction);
+// d is not initialised: the first ir_update of a correction overwrites it
 // `n` is a host upper bound of the row count; `n_dev` (optional) the exact device-side count.
 int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
                   const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s);
 // z = s o acc32; rz' = (s o r).acc32 (the bf16 s o r the GEMM consumed); beta = first ? 0 : rz'/rz; p = z + beta p -> (p_hi, p_lo)
 int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s);
-// q = acc32 + lam o p; alpha = rz / p.q; d += alpha p; r -= alpha q; rsb = bf16(s o r)
-int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, cudaStream_t s);
+// q = acc32 + lam o p; alpha = rz / p.q; d += alpha p (d = alpha p when `first`); r -= alpha q; rsb = bf16(s o r)
+int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, cudaStream_t s);
 // x = P[slot] + sigma d; P[slot] = x; X[state(slot)] = x
 int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, const int* n_dev,
               int T, int ld, cudaStream_t s);

@@ -202,9 +202,14 @@ __global__ void __launch_bounds__(1024) cg_compact_kernel(const int* __restrict_
   if (tid == 0) n_act[1] = base;
 }
 
-__global__ void cg_commit_count_kernel(int* n_act) { n_act[0] = n_act[1]; }
+// n_act = { current count, scratch (new count), "active set changed since the previous correction", "fresh list" }
+__global__ void cg_commit_count_kernel(int* n_act) {
+  n_act[2] = (n_act[1] != n_act[0]) || n_act[3];
+  n_act[3] = 0;
+  n_act[0] = n_act[1];
+}
 
-__global__ void cg_set_count_kernel(int* n_act, int n) { n_act[0] = n; n_act[1] = n; }
+__global__ void cg_set_count_kernel(int* n_act, int n) { n_act[0] = n; n_act[1] = n; n_act[2] = 1; n_act[3] = 1; }
 
 __global__ void cg_count_unconverged_kernel(const int* __restrict__ rows, int n_rows, const int* __restrict__ done,
                                             const int* __restrict__ iters, int* __restrict__ out) {
@@ -618,7 +623,7 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
           const int last = (it == inner - 1) ? 1 : 0;
           to.A0 = ib.p_hi; to.A1 = ib.p_lo;
           VGM_TRY(tc_gemm(to, st));
-          VGM_TRY(ir_update(ib, n, k.n_act, T, ld, last, st));
+          VGM_TRY(ir_update(ib, n, k.n_act, T, ld, last, it == 0 ? 1 : 0, st));
           if (last) break;
           VGM_TRY(tc_gemm(tp, st));
           VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 0, st));
