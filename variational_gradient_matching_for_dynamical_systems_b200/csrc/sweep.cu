@@ -605,7 +605,17 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
       }
       any = true;
       // n: host upper bound of the rows (k.n_act is exact); st: the stream to enqueue on / capture from
+      // experiment hook: VGM_IR_SCHEDULE="10,10,10,7" sets the CG steps of correction 0,1,2,... (last value repeats)
+      static int sched[16], n_sched = -1;
+      if (n_sched < 0) {
+        n_sched = 0;
+        if (const char* e = getenv("VGM_IR_SCHEDULE")) {
+          for (const char* q = e; *q && n_sched < 16;) { sched[n_sched++] = atoi(q); while (*q && *q != ',') ++q; if (*q) ++q; }
+        }
+      }
+      const int inner_now = n_sched > 0 ? max(1, sched[min(outer, n_sched - 1)]) : inner;
       auto enqueue_correction = [&](int n, cudaStream_t st) -> int {
+        const int inner = inner_now;
         IrBuf ib = k.ir;                                    // ir_dir reads p and writes q: swap after every call
         auto swap_pq = [&]() { std::swap(ib.p_hi, ib.q_hi); std::swap(ib.p_lo, ib.q_lo); };
         VGM_TRY(ir_inner_init(ib, cb.R, Lambda, cb.rr, k.act, n, k.n_act, T, ld, ops->G_shift, ops->precond_c, st));
@@ -641,7 +651,7 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
       memset(&key, 0, sizeof(key));
       key.r32 = k.ir.r32; key.act = k.act; key.n_act = k.n_act; key.G = ops->G_bf16; key.M = ops->M_bf16x2; key.X = X;
       key.Lambda = Lambda; key.R = cb.R; key.P = cb.P; key.rr = cb.rr; key.slot_state = slot_state;
-      key.n = min(k.n_rows, IR_GRAPH_MAX_ROWS); key.T = T; key.ld = ld; key.inner = inner;
+      key.n = min(k.n_rows, IR_GRAPH_MAX_ROWS); key.T = T; key.ld = ld; key.inner = inner_now;
       key.band_G = ops->band_G; key.band_M = ops->band_M_lp; key.shift = ops->G_shift; key.c = ops->precond_c;
       cudaGraphExec_t exec = nullptr;
       for (int i = 0; i < g_ir_graph_count; ++i)

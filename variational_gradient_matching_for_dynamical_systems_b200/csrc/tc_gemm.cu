@@ -306,7 +306,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
               make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0 && !(a.debug & 1)) tma_store_2d(&maps.out, sb, m0, rt * TC_BM + q * 32);
+        if (lane == 0) tma_store_2d(&maps.out, sb, m0, rt * TC_BM + q * 32);
         epi_buf ^= 1;
       }
       tc_fence_before();
@@ -407,9 +407,7 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
     VGM_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   const bool split = args.A1 != nullptr;
-  static const int dbg = getenv("VGM_TC_DEBUG") ? atoi(getenv("VGM_TC_DEBUG")) : 0;
-  TcGemmArgs largs = args;
-  largs.debug = dbg;
+  const TcGemmArgs& largs = args;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   VGM_TRY(make_bf16_map(&maps.a0, args.A0, args.n_rows, args.K, args.lda, TC_BM));

@@ -19,7 +19,6 @@ struct TcGemmArgs {
   int ldb;
   float* out;               // [n_rows][ldo] fp32
   int ldo;
-  int debug;                // timing experiments only (VGM_TC_DEBUG): 1 = skip the epilogue stores
 };
 
 int tc_gemm(const TcGemmArgs& args, cudaStream_t s);
