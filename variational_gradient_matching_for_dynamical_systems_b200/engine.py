@@ -179,6 +179,53 @@ class LocalProblem:
         return cls(model.K, model.K, model.ode_class, model.ode_idx, model.ode_state, hp, model.p)
 
 
+def pipeline_ranges(problem, n_chunks, theta_mode="reference"):
+    """State ranges for the pipelined ``vgm_iteration_host`` (vgm_model_tables.pipe_*), or None when the model /
+    plan does not allow it.  Pure host logic (NumPy): ``problem`` is a ``LocalProblem``.
+
+    Returns a dict with
+      kp  [n+1]  state boundaries of the ranges (multiples of 8): range c is copied in and STAGED as a whole
+      sp  [n+1]  hidden slots of each staged range
+      op  [n+1]  hidden slots of each SOLVE range: the systems whose state lies in [kp[c] - hx, kp[c+1] - hx); op[0]
+                 is the seam (slots of the states < hx, which the last range reads cyclically and which are solved last)
+      rp  [n+1]  the same boundaries as positions within dependency level 0
+      hx, hd     how far (in states, cyclically) the coefficients of a state reach into X and into D.X
+    Invariants (tests/test_host_logic.py): every state a range's staging reads is either not a hidden state solved
+    before that staging, i.e. all coefficients come from the sweep-start snapshot (proxies...py:191)."""
+    K, hp = problem.n_rows, problem.host_plan
+    hidden = np.asarray(hp.slot_state, dtype=np.int64)
+    if (n_chunks < 2 or theta_mode != "reference" or problem.n_stats_odes != K or problem.n_odes != K
+            or hp.n_hidden < 2 or np.any(np.diff(hidden) <= 0)
+            or not np.array_equal(problem.ode_state, np.arange(K))):
+        return None
+    arity = int(np.asarray(problem.ode_idx).size) // max(problem.n_odes, 1)
+
+    def cyc(d):
+        d = np.abs(d) % K
+        return np.minimum(d, K - d)
+    h = int(cyc(np.asarray(problem.ode_idx).reshape(K, arity).astype(np.int64) - np.arange(K)[:, None]).max()) if arity else 0
+    pair_slot = np.repeat(np.arange(hp.n_hidden), np.diff(hp.pair_ptr))
+    hc = int(cyc(hidden[pair_slot] - problem.ode_state[hp.pair_ode].astype(np.int64)).max()) if len(pair_slot) else 0
+    hx, hd = h + hc, hc
+    n_chunks = min(int(n_chunks), 32)
+    kp = (np.round(np.arange(n_chunks + 1) * K / n_chunks / 8).astype(np.int64) * 8)
+    kp[0], kp[-1] = 0, K
+    if np.any(np.diff(kp) < 2 * hx + 8) or hx <= 0:
+        return None
+    lvl0 = np.asarray(hp.level_slots[:hp.level_ptr[1]], dtype=np.int64)
+    later = np.asarray(hp.level_slots[hp.level_ptr[1]:], dtype=np.int64)
+    sp = np.searchsorted(hidden, kp)
+    if np.any(np.diff(lvl0) <= 0) or (len(later) and later.min() < sp[-2]):
+        return None
+    # solve ranges: shifted left by the halo; they start at the seam (states < hx) and end with the level
+    ko = kp - hx
+    ko[0], ko[-1] = hx, K
+    op = np.searchsorted(hidden, ko)
+    rp = np.searchsorted(lvl0, op)
+    rp[-1] = len(lvl0)
+    return dict(n=n_chunks, hx=hx, hd=hd, kp=kp, sp=sp, rp=rp, op=op)
+
+
 class VGMEngine:
     """Mean-field variational gradient matching on one GPU.
 
@@ -404,40 +451,12 @@ class VGMEngine:
         return self.last_info
 
     def _pipeline_tables(self, n_chunks):
-        """Chunk description for the pipelined ``vgm_iteration_host`` (vgm_model_tables.pipe_*), or None when the
-        model / plan does not allow it (see the conditions in include/vgm_b200.h)."""
-        K, hp, prob = self.K, self.problem.host_plan, self.problem
-        hidden = np.asarray(hp.slot_state, dtype=np.int64)
-        if (n_chunks < 2 or self.theta_mode != "reference" or prob.n_stats_odes != K or prob.n_odes != K
-                or hp.n_hidden < 2 or np.any(np.diff(hidden) <= 0)
-                or not np.array_equal(prob.ode_state, np.arange(K))):
+        """ctypes view of ``pipeline_ranges`` for this engine (or None)."""
+        pr = pipeline_ranges(self.problem, n_chunks, self.theta_mode)
+        if pr is None:
             return None
-        arity = int(np.asarray(prob.ode_idx).size) // max(prob.n_odes, 1)
-
-        def cyc(d):
-            d = np.abs(d) % K
-            return np.minimum(d, K - d)
-        h = int(cyc(np.asarray(prob.ode_idx).reshape(K, arity).astype(np.int64) - np.arange(K)[:, None]).max()) if arity else 0
-        pair_slot = np.repeat(np.arange(hp.n_hidden), np.diff(hp.pair_ptr))
-        hc = int(cyc(hidden[pair_slot] - prob.ode_state[hp.pair_ode].astype(np.int64)).max()) if len(pair_slot) else 0
-        hx, hd = h + hc, hc
-        n_chunks = min(int(n_chunks), 32)
-        kp = (np.round(np.arange(n_chunks + 1) * K / n_chunks / 8).astype(np.int64) * 8)
-        kp[0], kp[-1] = 0, K
-        if np.any(np.diff(kp) < 2 * hx + 8) or hx <= 0:
-            return None
-        lvl0 = np.asarray(hp.level_slots[:hp.level_ptr[1]], dtype=np.int64)
-        later = np.asarray(hp.level_slots[hp.level_ptr[1]:], dtype=np.int64)
-        sp = np.searchsorted(hidden, kp)
-        if np.any(np.diff(lvl0) <= 0) or (len(later) and later.min() < sp[-2]):
-            return None
-        # solve ranges: shifted left by the halo; they start at the seam (states < hx) and end with the level
-        ko = kp - hx
-        ko[0], ko[-1] = hx, K
-        op = np.searchsorted(hidden, ko)
-        rp = np.searchsorted(lvl0, op)
-        rp[-1] = len(lvl0)
-        return dict(n=n_chunks, hx=hx, hd=hd, kp=_host_i32(kp), sp=_host_i32(sp), rp=_host_i32(rp), op=_host_i32(op))
+        return dict(n=pr["n"], hx=pr["hx"], hd=pr["hd"], kp=_host_i32(pr["kp"]), sp=_host_i32(pr["sp"]),
+                    rp=_host_i32(pr["rp"]), op=_host_i32(pr["op"]))
 
     def iteration_host(self, X_host_KT: torch.Tensor, theta_host: torch.Tensor, X_host_out: torch.Tensor = None,
                        allow_unconverged=False, updated_rows_only=False, pipeline_chunks=0):
