@@ -28,6 +28,25 @@ def test_block_bounds_alignment():
     assert block_bounds(10, 3, align=2) == [0, 2, 6, 10]
 
 
+def test_weighted_bounds_give_the_chain_owner_fewer_states():
+    from variational_gradient_matching_for_dynamical_systems_b200.distributed import state_weights
+    K, world = 100000, 8
+    model = OdeModel.lorenz96(K)
+    hp = build_host_plan(model, list(range(1, K, 2)))
+    w = state_weights(model, hp, 1800)
+    assert w.sum() == K + 1800 and w[K - 1] == 1801          # the wrap-around state carries its level
+    b = block_bounds(K, world, align=2, weights=w)
+    sizes = np.diff(b)
+    assert b[0] == 0 and b[-1] == K and all(x % 2 == 0 for x in b)
+    assert sizes[-1] < sizes[0] - 1500 and max(sizes[:-1]) - min(sizes[:-1]) <= 2
+    tot = [w[b[g]:b[g + 1]].sum() for g in range(world)]
+    assert max(tot) - min(tot) <= 4
+    # an all-hidden chain (every level tiny) is not re-weighted; no weights = equal counts
+    hp2 = build_host_plan(OdeModel.lorenz96(64), list(range(64)))
+    assert np.all(state_weights(OdeModel.lorenz96(64), hp2, 1800) == 1.0)
+    assert block_bounds(10, 3, align=2) == [0, 2, 6, 10]
+
+
 @pytest.mark.parametrize("K,world,allhidden", [(24, 3, False), (20, 2, False), (12, 2, True), (30, 4, False)])
 def test_localize_reproduces_global_structure(K, world, allhidden):
     model = OdeModel.lorenz96(K)
