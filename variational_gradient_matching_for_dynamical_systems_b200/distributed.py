@@ -222,7 +222,8 @@ class DistributedVGMEngine:
         hp = build_host_plan(model, hidden, schedule=schedule)
         self.global_plan = hp
         tail = self.TAIL_LEVEL_COST_STATES if tail_level_cost_states is None else tail_level_cost_states
-        self.bounds = block_bounds(model.K, self.world, align=align, weights=state_weights(model, hp, tail))
+        self.bounds = block_bounds(model.K, self.world, align=align,
+                                   weights=state_weights(model, hp, tail) if tail > 0 else None)
         k0, k1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.loc = localize(model, hp, k0, k1)
         prob = LocalProblem(self.loc.n_rows, self.loc.n_stats_odes, self.loc.ode_class, self.loc.ode_idx,
