@@ -91,7 +91,8 @@ typedef struct {
   int band;
 } vgm_gemm_args;
 int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream);
-int vgm_dgemm_set_variant(int variant); /* tuning knob: tile configuration of the large-N GEMM (default 12) */
+int vgm_dgemm_set_variant(int variant); /* tile configuration of the large-N GEMM: 12 (default) = 64x64 x 4 CTAs/SM,
+                                           2 = 128x64 x 2, 0 = 128x128 x 1 */
 int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row of dot_out */
 /* Smallest b such that |B[i][j]| <= rel_threshold * max|B| whenever |i - j| > b (synchronises the stream).
  * With rel_threshold = 2^-64 the dropped part of any product is below half an ulp of the kept part's

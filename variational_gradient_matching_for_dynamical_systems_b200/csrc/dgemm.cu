@@ -226,25 +226,14 @@ static int launch_gemm(const vgm_gemm_args& a, cudaStream_t s) {
   return VGM_OK;
 }
 
-using CfgBig = GemmCfg<128, 128, 2, 4>;   // 256 threads, warp tile 64x32
-using CfgV1 = GemmCfg<128, 128, 4, 4>;             // 512 threads, warp tile 32x32
-using CfgV2 = GemmCfg<128, 64, 4, 2, 16, 3, 2>;    // 256 threads, warp tile 32x32, 2 CTAs/SM
-using CfgV3 = GemmCfg<128, 128, 2, 4, 32, 3, 1>;   // BK = 32
-using CfgV4 = GemmCfg<128, 128, 2, 4, 16, 3, 1>;   // default tile, 3 stages
-using CfgV5 = GemmCfg<64, 64, 2, 2, 16, 3, 3>;     // 128 threads, 3 CTAs/SM
-using CfgV6 = GemmCfg<128, 64, 2, 4, 16, 3, 2>;    // warp tile 64x16
-using CfgV7 = GemmCfg<64, 128, 2, 4, 16, 3, 2>;    // 64 rows x 128 columns
-using CfgV8 = GemmCfg<64, 64, 2, 2, 16, 2, 4>;     // 2 stages, 4 CTAs/SM
-using CfgV9 = GemmCfg<64, 64, 2, 2, 32, 2, 3>;     // BK = 32, 2 stages, 3 CTAs/SM
-using CfgV10 = GemmCfg<64, 64, 2, 2, 16, 2, 5>;    // 5 CTAs/SM
-using CfgV11 = GemmCfg<32, 64, 1, 2, 16, 2, 6>;    // 64 threads
-using CfgV12 = GemmCfg<64, 64, 4, 2, 16, 2, 4>;    // 256 threads, warp tile 16x32
-using CfgV13 = GemmCfg<128, 64, 8, 2, 16, 2, 2>;   // 512 threads, warp tile 16x32
-using CfgV14 = GemmCfg<64, 64, 4, 4, 16, 2, 2>;    // 512 threads, warp tile 16x16
-using CfgV15 = GemmCfg<32, 64, 2, 2, 16, 2, 7>;    // 128 threads, warp tile 16x32, 7 CTAs/SM
-using CfgV16 = GemmCfg<64, 64, 4, 2, 16, 3, 3>;    // V12 with 3 stages, 3 CTAs/SM
-static int g_variant = 12;  // 64x64 tiles, 256 threads (warp tile 16x32), 4 CTAs/SM: the short banded k loops leave a
-                            // large prologue/epilogue share, which more resident CTAs overlap (27.6 vs 22.4 TFLOP/s for 128x64 x2)
+// Tile configurations of the large-N GEMM (vgm_dgemm_set_variant / VGM_DGEMM_VARIANT).  Measured on the banded
+// residual GEMM of the bench (N = 50 000, M = K = 1000, band 146, B200): 128x128 x1 CTA/SM 15.8 TFLOP/s, 128x64 x2
+// 22.4, 64x64 (128 threads) x3 23.4, x4 26.0, 32x64 x7 27.7, 64x64 (256 threads, warp tile 16x32) x4 27.6 -- the
+// short banded k loop leaves a large prologue/epilogue share, which more resident CTAs overlap.
+using CfgBig = GemmCfg<128, 128, 2, 4>;            // variant 0: 256 threads, warp tile 64x32, 1 CTA/SM
+using CfgV2 = GemmCfg<128, 64, 4, 2, 16, 3, 2>;    // variant 2: 256 threads, warp tile 32x32, 2 CTAs/SM
+using CfgV12 = GemmCfg<64, 64, 4, 2, 16, 2, 4>;    // variant 12 (default): 256 threads, warp tile 16x32, 4 CTAs/SM
+static int g_variant = 12;
 using CfgMid = GemmCfg<64, 64, 2, 2>;     // 128 threads, warp tile 32x32
 using CfgThin = GemmCfg<16, 64, 1, 4>;    // 128 threads, warp tile 16x16 (few rows: halo / tail solves)
 
@@ -252,7 +241,7 @@ int gemm_dot_tiles(int M, int N) {
   // number of column tiles (= partial dot products per row) the chosen configuration produces
   if (N <= 16) return ceil_div(M, CfgThin::BN);
   if ((long long)ceil_div(N, 128) * ceil_div(M, 128) < 120) return ceil_div(M, CfgMid::BN);
-  return ceil_div(M, (g_variant == 2 || g_variant == 5 || g_variant == 6 || g_variant >= 8) ? 64 : 128);
+  return ceil_div(M, g_variant == 0 ? CfgBig::BN : 64);
 }
 
 static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s);
@@ -283,23 +272,9 @@ static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s) {
   if (a.N <= 16) return launch_gemm<CfgThin>(a, s);
   if ((long long)ceil_div(a.N, 128) * ceil_div(a.M, 128) < 120) return launch_gemm<CfgMid>(a, s);
   switch (g_variant) {
-    case 1: return launch_gemm<CfgV1>(a, s);
+    case 0: return launch_gemm<CfgBig>(a, s);
     case 2: return launch_gemm<CfgV2>(a, s);
-    case 3: return launch_gemm<CfgV3>(a, s);
-    case 4: return launch_gemm<CfgV4>(a, s);
-    case 5: return launch_gemm<CfgV5>(a, s);
-    case 6: return launch_gemm<CfgV6>(a, s);
-    case 7: return launch_gemm<CfgV7>(a, s);
-    case 8: return launch_gemm<CfgV8>(a, s);
-    case 9: return launch_gemm<CfgV9>(a, s);
-    case 10: return launch_gemm<CfgV10>(a, s);
-    case 11: return launch_gemm<CfgV11>(a, s);
-    case 12: return launch_gemm<CfgV12>(a, s);
-    case 13: return launch_gemm<CfgV13>(a, s);
-    case 14: return launch_gemm<CfgV14>(a, s);
-    case 15: return launch_gemm<CfgV15>(a, s);
-    case 16: return launch_gemm<CfgV16>(a, s);
-    default: return launch_gemm<CfgBig>(a, s);
+    default: return launch_gemm<CfgV12>(a, s);
   }
 }
 
