@@ -57,6 +57,11 @@ __device__ __forceinline__ void st_bf4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 __device__ __forceinline__ float bf_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// diagonal scaling of the preconditioner, s = bf16(sqrt((shift + c) / (Lambda + c))), from the FP32 copy of Lambda:
+// ir_inner_init stores it (s16) for ir_dir, ir_update recomputes the identical value instead of reading it
+__device__ __forceinline__ float precond_scale(float lam, float num, float c) {
+  return (c > 0.f) ? bf_round(sqrtf(num / (lam + c))) : 1.f;
+}
 // The GEMM writes columns < T only: whatever sits in the row padding of acc32 must not reach a dot product.
 __device__ __forceinline__ float4 ld_acc4(const float* p, int i, int T) {
   float4 v = ld_f4(p);
@@ -96,9 +101,8 @@ ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __rest
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const bool ok = i + e < T;
-        const double L = ok ? Lambda[os + i + e] : 0.0;
-        lp[e] = (float)L;
-        sp[e] = ok ? ((c > 0.0) ? bf_round((float)sqrt((shift + c) / (L + c))) : 1.f) : 0.f;
+        lp[e] = ok ? (float)Lambda[os + i + e] : 0.f;
+        sp[e] = ok ? precond_scale(lp[e], (float)(shift + c), (float)c) : 0.f;
       }
       *reinterpret_cast<float4*>(b.lam32 + oj + i) = lam;
       st_bf4(b.s16 + oj + i, sv);
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const 
 
 template <bool REG>
 __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const int* __restrict__ n_dev, int T, int ld,
-                                                               int last, int first) {
+                                                               int last, int first, float sc_num, float sc_c) {
   extern __shared__ float ir_sm[];       // p and q of this row (!REG)
   __shared__ double red[40];
   float* sp = ir_sm;
@@ -241,11 +245,12 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
   if (n_dev && j >= *n_dev) return;
   const size_t o = (size_t)j * ld;
   float part = 0.f;
-  float4 preg = make_float4(0.f, 0.f, 0.f, 0.f), qreg = preg;
+  float4 preg = make_float4(0.f, 0.f, 0.f, 0.f), qreg = preg, lreg4 = preg;
   IR_ROW_LOOP(i, T) {
     const float4 h = ld_bf4(b.p_hi + o + i), l = ld_bf4(b.p_lo + o + i);
     const float4 acc = ld_acc4(b.acc32 + o + i, i, T);
     const float4 lam = ld_f4(b.lam32 + o + i);
+    if (REG) lreg4 = lam;
     const float4 p = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
     const float4 q = make_float4(fmaf(lam.x, p.x, acc.x), fmaf(lam.y, p.y, acc.y), fmaf(lam.z, p.z, acc.z),
                                  fmaf(lam.w, p.w, acc.w));
@@ -256,12 +261,12 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
     part += fmaf(p.x, q.x, fmaf(p.y, q.y, fmaf(p.z, q.z, p.w * q.w)));
   }
   // REG: issue the loads of the second phase before the row-wide reduction so their latency hides behind it
-  float4 dreg = make_float4(0.f, 0.f, 0.f, 0.f), rreg = preg, sreg = preg;
+  float4 dreg = make_float4(0.f, 0.f, 0.f, 0.f), rreg = preg;
   if (REG) {
     const int i = 4 * threadIdx.x;
     if (i < T) {
       if (!first) dreg = ld_f4(b.d32 + o + i);             // first step of a correction: d = alpha p
-      if (!last) { rreg = ld_f4(b.r32 + o + i); sreg = ld_bf4(b.s16 + o + i); }
+      if (!last) rreg = ld_f4(b.r32 + o + i);
     }
   }
   const double pq = block_sum((double)part, red);
@@ -276,7 +281,9 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
       float4 r = REG ? rreg : ld_f4(b.r32 + o + i);
       r.x = fmaf(-alpha, q.x, r.x); r.y = fmaf(-alpha, q.y, r.y); r.z = fmaf(-alpha, q.z, r.z); r.w = fmaf(-alpha, q.w, r.w);
       *reinterpret_cast<float4*>(b.r32 + o + i) = r;
-      const float4 sv = REG ? sreg : ld_bf4(b.s16 + o + i);
+      const float4 lam = REG ? lreg4 : ld_f4(b.lam32 + o + i);
+      const float4 sv = make_float4(precond_scale(lam.x, sc_num, sc_c), precond_scale(lam.y, sc_num, sc_c),
+                                    precond_scale(lam.z, sc_num, sc_c), precond_scale(lam.w, sc_num, sc_c));
       st_bf4(b.rsb + o + i, make_float4(sv.x * r.x, sv.y * r.y, sv.z * r.z, sv.w * r.w));
     }
   }
@@ -319,12 +326,14 @@ int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cu
   return VGM_OK;
 }
 
-int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, cudaStream_t s) {
+int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, double shift, double c,
+              cudaStream_t s) {
   if (n <= 0) return VGM_OK;
-  // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4, s16 2); writes d32 4, (r32 4, rsb 2)
-  ProfScope prof(PROF_IR_UPDATE, 0.0, (double)n * T * ((last ? 20.0 : 32.0) - (first ? 4.0 : 0.0)), s);
-  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, last, first);
-  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, last, first);
+  // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4); writes d32 4, (r32 4, rsb 2)
+  ProfScope prof(PROF_IR_UPDATE, 0.0, (double)n * T * ((last ? 20.0 : 30.0) - (first ? 4.0 : 0.0)), s);
+  const float sc_num = (float)(shift + c), sc_c = (float)c;
+  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, last, first, sc_num, sc_c);
+  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, last, first, sc_num, sc_c);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }

@@ -27,7 +27,8 @@ int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const d
 // z = s o acc32; rz' = (s o r).acc32 (the bf16 s o r the GEMM consumed); beta = first ? 0 : rz'/rz; p = z + beta p -> (p_hi, p_lo)
 int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s);
 // q = acc32 + lam o p; alpha = rz / p.q; d += alpha p (d = alpha p when `first`); r -= alpha q; rsb = bf16(s o r)
-int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, cudaStream_t s);
+int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, double shift, double c,
+              cudaStream_t s);
 // x = P[slot] + sigma d; P[slot] = x; X[state(slot)] = x
 int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const int* act, int n, const int* n_dev,
               int T, int ld, cudaStream_t s);

@@ -633,7 +633,7 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
           const int last = (it == inner - 1) ? 1 : 0;
           to.A0 = ib.p_hi; to.A1 = ib.p_lo;
           VGM_TRY(tc_gemm(to, st));
-          VGM_TRY(ir_update(ib, n, k.n_act, T, ld, last, it == 0 ? 1 : 0, st));
+          VGM_TRY(ir_update(ib, n, k.n_act, T, ld, last, it == 0 ? 1 : 0, ops->G_shift, ops->precond_c, st));
           if (last) break;
           VGM_TRY(tc_gemm(tp, st));
           VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 0, st));
