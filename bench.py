@@ -56,9 +56,15 @@ def parse():
     ap.add_argument("--inner-iters", type=int, default=10)
     ap.add_argument("--tol", type=float, default=1e-13)
     ap.add_argument("--optimistic-passes", type=int, default=4)
-    ap.add_argument("--pipeline-chunks", type=int, default=3, help="e2e: state ranges whose copies overlap the compute")
+    ap.add_argument("--pipeline-chunks", default="0.12,0.5,0.88,1.0",
+                    help="e2e: state ranges whose copies overlap the compute: a count (equal ranges) or the upper ends "
+                         "of the ranges as fractions; a short first range starts the compute early, a short last "
+                         "one shortens the final copy-out; 0 = no pipelining")
     ap.add_argument("--no-profile", action="store_true", help="skip the second, per-kernel-instrumented timed region")
-    return ap.parse_args()
+    args = ap.parse_args()
+    pc = str(args.pipeline_chunks)
+    args.pipeline_chunks = tuple(float(v) for v in pc.split(",")) if "," in pc else int(pc)
+    return args
 
 
 # ----------------------------------------------------------------------------------------------

@@ -47,6 +47,18 @@ def test_pipeline_ranges_cover_everything_and_keep_the_snapshot(K, n):
         assert st.size == 0 or st.max() < kp[c + 1]
 
 
+def test_pipeline_ranges_with_uneven_fractions():
+    K = 100000
+    prob = _problem(K, np.arange(1, K, 2))
+    pr = pipeline_ranges(prob, (0.15, 0.55, 0.9, 1.0))
+    assert pr["n"] == 4 and list(pr["kp"]) == [0, 15000, 55000, 90000, 100000]
+    assert pr["rp"][-1] == prob.host_plan.level_ptr[1] and np.all(np.diff(pr["rp"]) > 0)
+    with pytest.raises(ValueError):
+        pipeline_ranges(prob, (0.5, 0.4, 1.0))
+    with pytest.raises(ValueError):
+        pipeline_ranges(prob, (0.5, 0.9))
+
+
 def test_pipeline_ranges_refuse_what_they_cannot_handle():
     K = 96
     prob = _problem(K, np.arange(1, K, 2))

@@ -181,7 +181,9 @@ class LocalProblem:
 
 def pipeline_ranges(problem, n_chunks, theta_mode="reference"):
     """State ranges for the pipelined ``vgm_iteration_host`` (vgm_model_tables.pipe_*), or None when the model /
-    plan does not allow it.  Pure host logic (NumPy): ``problem`` is a ``LocalProblem``.
+    plan does not allow it.  Pure host logic (NumPy): ``problem`` is a ``LocalProblem``.  ``n_chunks`` is either
+    the number of equal ranges or the increasing upper ends of the ranges as fractions of the states, ending in
+    1.0 (a short first range lets the compute start early, a short last one shortens the final copy-out).
 
     Returns a dict with
       kp  [n+1]  state boundaries of the ranges (multiples of 8): range c is copied in and STAGED as a whole
@@ -194,6 +196,12 @@ def pipeline_ranges(problem, n_chunks, theta_mode="reference"):
     before that staging, i.e. all coefficients come from the sweep-start snapshot (proxies...py:191)."""
     K, hp = problem.n_rows, problem.host_plan
     hidden = np.asarray(hp.slot_state, dtype=np.int64)
+    fractions = None
+    if not np.isscalar(n_chunks):
+        fractions = np.asarray(list(n_chunks), dtype=np.float64)
+        if len(fractions) < 2 or np.any(np.diff(fractions) <= 0) or fractions[0] <= 0 or abs(fractions[-1] - 1.0) > 1e-12:
+            raise ValueError("range ends must increase and finish at 1.0")
+        n_chunks = len(fractions)
     if (n_chunks < 2 or theta_mode != "reference" or problem.n_stats_odes != K or problem.n_odes != K
             or hp.n_hidden < 2 or np.any(np.diff(hidden) <= 0)
             or not np.array_equal(problem.ode_state, np.arange(K))):
@@ -208,7 +216,8 @@ def pipeline_ranges(problem, n_chunks, theta_mode="reference"):
     hc = int(cyc(hidden[pair_slot] - problem.ode_state[hp.pair_ode].astype(np.int64)).max()) if len(pair_slot) else 0
     hx, hd = h + hc, hc
     n_chunks = min(int(n_chunks), 32)
-    kp = (np.round(np.arange(n_chunks + 1) * K / n_chunks / 8).astype(np.int64) * 8)
+    ends = np.arange(n_chunks + 1) / n_chunks if fractions is None else np.concatenate([[0.0], fractions])
+    kp = (np.round(ends * K / 8).astype(np.int64) * 8)
     kp[0], kp[-1] = 0, K
     if np.any(np.diff(kp) < 2 * hx + 8) or hx <= 0:
         return None
@@ -470,9 +479,10 @@ class VGMEngine:
         model does not allow it; ``self.last_pipeline`` tells which ran)."""
         if X_host_out is None:
             X_host_out = X_host_KT
-        if pipeline_chunks and pipeline_chunks not in self._pipe_cache:
-            self._pipe_cache[pipeline_chunks] = self._pipeline_tables(pipeline_chunks)
-        pt = self._pipe_cache.get(pipeline_chunks) if pipeline_chunks else None
+        pkey = pipeline_chunks if np.isscalar(pipeline_chunks) else tuple(pipeline_chunks)
+        if pkey and pkey not in self._pipe_cache:
+            self._pipe_cache[pkey] = self._pipeline_tables(pipeline_chunks)
+        pt = self._pipe_cache.get(pkey) if pkey else None
         self.last_pipeline = pt["n"] if pt else 0
         m = self._mt
         m.pipe_chunks = 0
