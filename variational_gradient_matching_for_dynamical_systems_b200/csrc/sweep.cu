@@ -3,15 +3,18 @@
 //
 // For hidden state u the reference forms a dense T x T system
 //     (B_uu^T B_uu + diag(Lambda_u)) x_u = rhs_u,   B_uu = diag(R_uu) - D        (:229-232, :245, :262)
-// and calls LAPACK gesv on it.  Here every state of a dependency level is solved together by
-// (preconditioned) conjugate gradients whose operator application is one large FP64 DMMA GEMM
-// over all states:  Q = P M^T + Lambda o P  (shared M when R_uu is a constant, e.g. Lorenz96
-// where R_uu = -1), or two GEMMs with D and D^T when R_uu varies per state.  The optional
-// preconditioner is the shared matrix G = (M + shift I)^-1 (another GEMM).  Residuals are
-// driven to ||r|| <= tol ||rhs|| per state (default 1e-13), i.e. far below the 1e-9 parity
-// tolerance, and the sequential Gauss-Seidel semantics of the reference (:185 alias, :225 live
-// read) are reproduced by solving dependency levels in order and patching rhs with the freshly
-// updated D x_k between levels.
+// and calls LAPACK gesv on it.  Here every state of a dependency level is solved together:
+//   * shared system matrix (R_uu constant, e.g. -1 for Lorenz96: M = (cI - D)^T (cI - D)): mixed-precision
+//     iterative refinement, ir_solve -- FP64 residuals r = rhs - x M^T - Lambda o x as ONE banded DMMA GEMM per
+//     pass, corrections by FP32 preconditioned CG whose operator products are bf16-split tcgen05 GEMMs
+//     (tc_gemm.cu) and whose vector work lives in refine.cu; systems it cannot contract (too ill-conditioned)
+//     are finished by
+//   * FP64 preconditioned CG on the DMMA pipe, pcg_solve -- operator Q = P M^T + Lambda o P (one GEMM), or two
+//     GEMMs with D and D^T when R_uu varies per state; optional preconditioner G = (M + shift I)^-1.
+// Residuals are driven to ||r|| <= tol ||rhs|| per state (default 1e-13), i.e. far below the 1e-9 parity
+// tolerance, and the sequential Gauss-Seidel semantics of the reference (:185 alias, :225 live read) are
+// reproduced by solving dependency levels in order and patching rhs with the freshly updated D x_k between
+// levels.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
