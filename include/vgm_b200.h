@@ -305,6 +305,8 @@ typedef struct {
   const int* pipe_slot_ptr_host;
   const int* pipe_row_ptr_host;
   const int* pipe_out_slot_ptr_host;
+  const int* pipe_last_rows; /* optional DEVICE array: the level-0 slots of the last solve range followed by the seam's
+                                (row_ptr[n] - row_ptr[n-1] + row_ptr[0] entries): one solve instead of two */
 } vgm_model_tables;
 size_t vgm_iteration_ws_bytes(const vgm_model_tables* model, const vgm_sweep_plan* plan);
 int vgm_iteration_device(const vgm_program* prog, const vgm_model_tables* model, const vgm_sweep_plan* plan,

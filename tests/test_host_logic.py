@@ -39,6 +39,7 @@ def test_pipeline_ranges_cover_everything_and_keep_the_snapshot(K, n):
         lo, hi = kp[c] - hx, kp[c + 1] + hx            # states range c's staging may read
         reach = np.arange(lo, hi) % K
         assert not np.intersect1d(done_states, reach).size, c
+    assert np.array_equal(pr["last_rows"], np.concatenate([lvl0[rp[-2]:], lvl0[:rp[0]]]))
     # the seam (solved last) is exactly the hidden states below hx
     assert np.array_equal(state_of[lvl0[:rp[0]]], hidden[hidden < hx])
     # a solve range only needs coefficients that were staged by then

@@ -77,7 +77,8 @@ class ModelTables(C.Structure):
                 ("out_row0", C.c_int), ("out_row_stride", C.c_int), ("out_n_rows", C.c_int),
                 ("pipe_chunks", C.c_int), ("pipe_halo_x", C.c_int), ("pipe_halo_dx", C.c_int),
                 ("pipe_state_ptr_host", C.POINTER(C.c_int)), ("pipe_slot_ptr_host", C.POINTER(C.c_int)),
-                ("pipe_row_ptr_host", C.POINTER(C.c_int)), ("pipe_out_slot_ptr_host", C.POINTER(C.c_int))]
+                ("pipe_row_ptr_host", C.POINTER(C.c_int)), ("pipe_out_slot_ptr_host", C.POINTER(C.c_int)),
+                ("pipe_last_rows", c_ip)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/vgm_b200.h

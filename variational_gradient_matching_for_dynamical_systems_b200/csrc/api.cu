@@ -29,6 +29,9 @@ int state_sweep_prepare_range(const vgm_program* prog, const vgm_sweep_plan* pl,
                               size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s);
 int state_sweep_level_rows(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts, double* X,
                            int lev, int r0, int r1, void* ws, size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s);
+int state_sweep_row_list(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts, double* X,
+                         const int* rows_dev, int n_rows, void* ws, size_t ws_bytes, vgm_sweep_info* info,
+                         cudaStream_t s);
 int state_sweep_level_full(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts, double* X,
                            int lev, void* ws, size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s);
 
@@ -276,9 +279,14 @@ static int iteration_host_pipelined(const vgm_program* prog, const vgm_model_tab
   static const bool dbg = getenv("VGM_DEBUG") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  // with pipe_last_rows (the last range's systems followed by the seam's) the seam joins the last solve
+  const bool seam_joined = model->pipe_last_rows != nullptr && seam_rows > 0;
   for (int c = 0; c < C; ++c) {
     VGM_TRY(stage(c));
-    int r = state_sweep_level_rows(plan, ops, opts, X, 0, rp[c], rp[c + 1], ws_sweep, ws_sweep_bytes, info, s);
+    int r = (c == C - 1 && seam_joined)
+                ? state_sweep_row_list(plan, ops, opts, X, model->pipe_last_rows, rp[C] - rp[C - 1] + seam_rows, ws_sweep,
+                                       ws_sweep_bytes, info, s)
+                : state_sweep_level_rows(plan, ops, opts, X, 0, rp[c], rp[c + 1], ws_sweep, ws_sweep_bytes, info, s);
     if (dbg) fprintf(stderr, "[vgm] pipeline: range %d (%d systems) solved at %.2f ms\n", c, rp[c + 1] - rp[c], ms_now());
     if (r == VGM_ENOTCONV) rc = r; else if (r != VGM_OK) return r;
     if (c + 1 < C) {                                      // the last range goes out with the seam and the later levels
@@ -288,7 +296,7 @@ static int iteration_host_pipelined(const vgm_program* prog, const vgm_model_tab
                             op[c + 1], R.s_out));
     }
   }
-  {
+  if (!seam_joined) {
     int r = state_sweep_level_rows(plan, ops, opts, X, 0, 0, seam_rows, ws_sweep, ws_sweep_bytes, info, s);
     if (r == VGM_ENOTCONV) rc = r; else if (r != VGM_OK) return r;
   }

@@ -907,6 +907,22 @@ int state_sweep_level_rows(const vgm_sweep_plan* pl, const vgm_operators* ops, c
   return rc;
 }
 
+// Solve an explicit list of level-0 systems (device array of hidden slots); used by the pipelined host iteration
+// to solve its last range together with the cyclic seam.
+int state_sweep_row_list(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts, double* X,
+                         const int* rows_dev, int n_rows, void* ws, size_t ws_bytes, vgm_sweep_info* info,
+                         cudaStream_t s) {
+  VGM_REQUIRE(pl && ops && X && rows_dev && n_rows >= 0 && n_rows <= pl->n_hidden, "row list");
+  if (n_rows == 0) return VGM_OK;
+  SweepWs w;
+  VGM_TRY(sweep_carve(ws, ws_bytes, pl, w));
+  Counters cnt;
+  int rc = pcg_solve(ops, pl->ruu_const, w.Ruu, w.Lambda, w.rhs, X, pl->slot_state, pl->slot_has_self, rows_dev, n_rows,
+                     pl->n_hidden, pl->T, pl->ld, opts, w.pcg, info, cnt, s);
+  if (info) { info->gemm_calls += cnt.gemm; info->kernel_launches += cnt.launches; }
+  return rc;
+}
+
 // Phase 2, once per dependency level (in order): refresh D x_k of the states updated in the
 // previous level that this level reads live (:225), patch rhs, solve the level's systems.
 static int state_sweep_level(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts,

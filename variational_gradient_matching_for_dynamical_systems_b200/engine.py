@@ -232,7 +232,8 @@ def pipeline_ranges(problem, n_chunks, theta_mode="reference"):
     op = np.searchsorted(hidden, ko)
     rp = np.searchsorted(lvl0, op)
     rp[-1] = len(lvl0)
-    return dict(n=n_chunks, hx=hx, hd=hd, kp=kp, sp=sp, rp=rp, op=op)
+    last_rows = np.concatenate([lvl0[rp[-2]:], lvl0[:rp[0]]]).astype(np.int32)
+    return dict(n=n_chunks, hx=hx, hd=hd, kp=kp, sp=sp, rp=rp, op=op, last_rows=last_rows)
 
 
 class VGMEngine:
@@ -465,7 +466,7 @@ class VGMEngine:
         if pr is None:
             return None
         return dict(n=pr["n"], hx=pr["hx"], hd=pr["hd"], kp=_host_i32(pr["kp"]), sp=_host_i32(pr["sp"]),
-                    rp=_host_i32(pr["rp"]), op=_host_i32(pr["op"]))
+                    rp=_host_i32(pr["rp"]), op=_host_i32(pr["op"]), last_rows=_i32(pr["last_rows"], self.dev))
 
     def iteration_host(self, X_host_KT: torch.Tensor, theta_host: torch.Tensor, X_host_out: torch.Tensor = None,
                        allow_unconverged=False, updated_rows_only=False, pipeline_chunks=0):
@@ -492,6 +493,7 @@ class VGMEngine:
             m.pipe_slot_ptr_host = C.cast(pt["sp"], C.POINTER(C.c_int))
             m.pipe_row_ptr_host = C.cast(pt["rp"], C.POINTER(C.c_int))
             m.pipe_out_slot_ptr_host = C.cast(pt["op"], C.POINTER(C.c_int))
+            m.pipe_last_rows = pt["last_rows"].data_ptr()
             self._pipe_keep = pt
         self._mt.out_n_rows = 0
         h = self.plan.hidden
