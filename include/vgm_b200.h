@@ -148,6 +148,14 @@ int vgm_param_stats(const vgm_program* prog, const double* X, const double* DX, 
                     double* stats, void* ws, size_t ws_bytes, vgm_stream_t stream);
 int vgm_param_solve(const double* stats, int n_param, double* theta, vgm_stream_t stream);
 
+/* Opt-in parameter "covariance"  cov = sum_k B_k^T A B_k  (p x p, row-major, device), the quantity the
+ * reference computes at proxies...py:79 and never returns.  A = eps_cov [T][ld].  The B rows are
+ * materialised in chunks of ODE rows, multiplied by A with the DMMA GEMM and reduced deterministically. */
+size_t vgm_param_cov_ws_bytes(int n_odes, int ld, int n_param);
+int vgm_param_cov(const vgm_program* prog, const double* X, const double* A, int ld, int T, int n_odes,
+                  const int* ode_class, const int* ode_idx, double* cov, void* ws, size_t ws_bytes,
+                  vgm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * P4  proxy_for_ind_states (optimizer='analytical'), proxies...py:185-262
  * The sweep plan (index tables on the device, built once by the host from state_couplings).

@@ -480,6 +480,38 @@ def test_state_cov_vs_oracle(pkg):
     assert relerr(cov, vo.lorenz96_state_cov(g["X0"], 3, g["D"], g["A"])) < TOL
 
 
+@pytest.mark.parametrize("builtin", [True, False])
+@pytest.mark.parametrize("tag", ["lorenz96_K10_T40", "lorenz96_K12_T100", "lotka_volterra_T50", "lorenz_attractor_T150",
+                                 "protein_transduction_T99"])
+def test_param_cov_vs_reference_golden(pkg, tag, builtin):
+    """Parameter covariance sum_k B_k^T A B_k (proxies...py:79) against the golden made from the live reference's own
+    B callables, and against the oracle."""
+    g = load(tag + ".npz")
+    if "lines" in g.files:
+        if builtin:
+            pytest.skip("no built-in program for this model")
+        lines, params = [str(s) for s in g["lines"]], [str(s) for s in g["params"]]
+        eng = _engine_from_golden(pkg, g, lines, params, theta_mode="proxy")
+    else:
+        eng = _engine_from_golden(pkg, g, vo.lorenz96_ode_lines(len(g["names"])), ["_alpha"], builtin=builtin)
+    cov = eng.param_cov()
+    gold = load("param_cov.npz")[tag]
+    assert cov.shape == gold.shape
+    assert relerr(cov, gold) < TOL
+
+
+def test_param_cov_chunked_over_ode_rows(pkg):
+    """More ODE rows than one pass holds (8192 / p): Lorenz96 K=9000, B == 1, so cov = K * 1^T A 1."""
+    p, _lib, engine = pkg
+    K, T = 9000, 64
+    t = np.arange(T) * 0.05
+    D, A, *_ = vo.kernel_function(t, t[:2], "rbf", [0.0625, 1.0])
+    model = p.OdeModel(vo.lorenz96_ode_lines(K), ["_x_%d" % (i + 1) for i in range(K)], ["_alpha"])
+    eng = engine.VGMEngine(model, D, A, hidden=list(range(1, K, 2)))
+    eng.set_states(np.random.default_rng(0).normal(size=(T, K)))
+    assert relerr(eng.param_cov(), np.array([[K * A.sum()]])) < TOL
+
+
 def test_colour_schedule_opt_in(pkg):
     """Opt-in multi-colour schedule (north_star: reported separately, own tolerance).  It is not
     the reference's update order, so no 1e-9 parity is claimed; the stated tolerance is on the

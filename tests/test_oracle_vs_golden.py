@@ -110,6 +110,22 @@ def test_fit_state_observations():
     assert relerr(mean, g["mean"]) < 1e-10
 
 
+@pytest.mark.parametrize("tag", ["lorenz96_K10_T40", "lorenz96_K12_T100", "lorenz96_K8_T30_allhidden",
+                                 "lotka_volterra_T50", "lorenz_attractor_T150", "protein_transduction_T99"])
+def test_param_cov_matches_reference_statements(tag):
+    """global_cov of proxies...py:79 (dropped by the reference): golden made by oracle/make_golden_param_cov.py from the
+    live reference's own B callables."""
+    g = load(tag + ".npz")
+    if "lines" in g.files:
+        lin, _ = _lin_from_golden(g, [str(s) for s in g["lines"]], [str(s) for s in g["params"]])
+    else:
+        lin, _ = _lin_from_golden(g, vo.lorenz96_ode_lines(len(g["names"])), ["_alpha"])
+    Cth = vo.theta_step(g["X0"], lin, g["D"], g["A"])[3]
+    gold = load("param_cov.npz")[tag]
+    assert Cth.shape == gold.shape
+    assert relerr(Cth, gold) < 1e-12
+
+
 def test_state_cov_closed_form_matches_general():
     g = load("lorenz96_K10_T40.npz")
     lin, names = _lin_from_golden(g, vo.lorenz96_ode_lines(10), ["_alpha"])

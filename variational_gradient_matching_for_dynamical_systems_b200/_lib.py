@@ -111,6 +111,9 @@ SIGNATURES = {
     "vgm_param_stats": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp,
                                   C.c_size_t, C.c_void_p]),
     "vgm_param_solve": (C.c_int, [c_dp, C.c_int, c_dp, C.c_void_p]),
+    "vgm_param_cov_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "vgm_param_cov": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_dp, c_dp, C.c_size_t,
+                                C.c_void_p]),
     "vgm_state_sweep_ws_bytes": (C.c_size_t, [_P(SweepPlan)]),
     "vgm_state_sweep": (C.c_int, [C.c_void_p, _P(SweepPlan), _P(Operators), _P(SolverOpts), c_dp, c_dp, c_dp, c_dp,
                                   C.c_size_t, _P(SweepInfo), C.c_void_p]),

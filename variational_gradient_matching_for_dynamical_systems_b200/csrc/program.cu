@@ -43,6 +43,7 @@ struct vgm_program {
   cudaKernel_t k_stats;
   cudaKernel_t k_assemble;
   cudaKernel_t k_pair_R;
+  cudaKernel_t k_param_B;
 };
 
 namespace vgm {
@@ -74,6 +75,8 @@ static int driver_launch_grid(cudaKernel_t k, unsigned grid, unsigned block, voi
   return driver_launch(k, grid, block, args, s);
 }
 
+int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s);
+
 static int prog_threads(int T) { return max(64, min(256, (T + 31) / 32 * 32)); }
 
 int program_param_stats(const vgm_program* prog, const double* X, const double* DX, int ld, int T, int n_odes,
@@ -91,6 +94,18 @@ int program_param_stats(const vgm_program* prog, const double* X, const double* 
   void* args[] = {(void*)&X, (void*)&DX, (void*)&ld, (void*)&T, (void*)&n_odes, (void*)&ode_class,
                   (void*)&ode_idx, (void*)&ode_state, (void*)&partial};
   return driver_launch(prog->k_stats, grid, block, args, s);
+}
+
+int program_param_B(const vgm_program* prog, const double* X, int ld, int T, int n_rows, const int* ode_class,
+                    const int* ode_idx, double* Bout, cudaStream_t s) {
+  const int block = prog_threads(T);
+  if (prog->builtin) {
+    lorenz96_prog::vgm_lorenz96_param_B<<<n_rows, block, 0, s>>>(X, ld, T, n_rows, ode_class, ode_idx, Bout);
+    VGM_LAUNCH_OK();
+    return VGM_OK;
+  }
+  void* args[] = {(void*)&X, (void*)&ld, (void*)&T, (void*)&n_rows, (void*)&ode_class, (void*)&ode_idx, (void*)&Bout};
+  return driver_launch(prog->k_param_B, n_rows, block, args, s);
 }
 
 int program_state_assemble(const vgm_program* prog, const vgm_sweep_plan* pl, const double* X, const double* DX0,
@@ -156,6 +171,38 @@ __global__ void __launch_bounds__(256) stats_reduce_kernel(const double* __restr
   }
 }
 
+// Parameter covariance (proxies...py:79, computed and dropped by the reference): per-CTA partials of
+//   cov[i][l] = sum_j sum_t B_{j,i}(t) (A B_{j,l})(t)   over COV_ROWS ODE rows per CTA, all p x p pairs
+constexpr int COV_ROWS = 8;
+__global__ void __launch_bounds__(256) cov_partial_kernel(const double* __restrict__ Bm, const double* __restrict__ AB,
+                                                          int ld, int T, int n_rows, int p,
+                                                          double* __restrict__ partial) {
+  __shared__ double red[40];
+  const int j0 = blockIdx.x * COV_ROWS, j1 = min(n_rows, j0 + COV_ROWS);
+  for (int q = 0; q < p * p; ++q) {
+    const int i = q / p, l = q % p;
+    double v = 0.0;
+    for (int j = j0; j < j1; ++j) {
+      const double* bi = Bm + ((size_t)j * p + i) * ld;
+      const double* al = AB + ((size_t)j * p + l) * ld;
+      for (int t = threadIdx.x; t < T; t += blockDim.x) v += bi[t] * al[t];
+    }
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * p * p + q] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) cov_reduce_kernel(const double* __restrict__ partial, int n_part, int nq,
+                                                         double* __restrict__ cov) {
+  __shared__ double red[40];
+  for (int q = 0; q < nq; ++q) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) v += partial[(size_t)i * nq + q];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) cov[q] = v;
+  }
+}
+
 // P3: theta = solve(S, m) for constraints=None (proxies...py:93): Gaussian elimination with
 // partial pivoting (what LAPACK gesv does) in one thread; p is a handful.
 __global__ void param_solve_kernel(const double* __restrict__ stats, int p, double* __restrict__ theta) {
@@ -203,6 +250,7 @@ extern "C" int vgm_program_builtin(const char* name, vgm_program** out) {
   p->k_stats = nullptr;
   p->k_assemble = nullptr;
   p->k_pair_R = nullptr;
+  p->k_param_B = nullptr;
   *out = p;
   return VGM_OK;
 }
@@ -224,6 +272,7 @@ extern "C" int vgm_program_load(const void* cubin_host, size_t size, int n_param
   e = cudaLibraryGetKernel(&p->k_stats, p->lib, "vgm_prog_param_stats");
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->k_assemble, p->lib, "vgm_prog_state_assemble");
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->k_pair_R, p->lib, "vgm_prog_state_pair_R");
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->k_param_B, p->lib, "vgm_prog_param_B");
   if (e != cudaSuccess) {
     set_error("cudaLibraryGetKernel: %s", cudaGetErrorString(e));
     cudaLibraryUnload(p->lib);
@@ -276,6 +325,51 @@ extern "C" int vgm_param_stats(const vgm_program* prog, const double* X, const d
   double* partial = (double*)ws;
   VGM_TRY(program_param_stats(prog, X, DX, ld, T, n_odes, ode_class, ode_idx, ode_state, partial, s));
   stats_reduce_kernel<<<1, 256, 0, s>>>(partial, ceil_div(n_odes, 8), prog->n_param, stats);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
+
+// ODE rows handled per pass of vgm_param_cov: bounds the two [rows * p][ld] scratch matrices
+static int cov_chunk_rows(int n_odes, int n_param) {
+  const int cap = max(COV_ROWS, (8192 / n_param) / COV_ROWS * COV_ROWS);
+  return min(cap, ceil_div(n_odes, COV_ROWS) * COV_ROWS);
+}
+
+extern "C" size_t vgm_param_cov_ws_bytes(int n_odes, int ld, int n_param) {
+  const size_t partial = align_up((size_t)ceil_div(n_odes, COV_ROWS) * n_param * n_param * sizeof(double), 256);
+  const size_t mat = align_up((size_t)cov_chunk_rows(n_odes, n_param) * n_param * ld * sizeof(double), 256);
+  return partial + 2 * mat;
+}
+
+extern "C" int vgm_param_cov(const vgm_program* prog, const double* X, const double* A, int ld, int T, int n_odes,
+                             const int* ode_class, const int* ode_idx, double* cov, void* ws, size_t ws_bytes,
+                             vgm_stream_t stream) {
+  VGM_REQUIRE(prog && X && A && cov && ode_class && ode_idx, "null argument");
+  VGM_REQUIRE(n_odes > 0 && T > 0 && ld >= T, "shape");
+  const int p = prog->n_param;
+  VGM_REQUIRE(ws && ws_bytes >= vgm_param_cov_ws_bytes(n_odes, ld, p), "workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ch = cov_chunk_rows(n_odes, p);
+  const size_t partial_bytes = align_up((size_t)ceil_div(n_odes, COV_ROWS) * p * p * sizeof(double), 256);
+  const size_t mat_bytes = align_up((size_t)ch * p * ld * sizeof(double), 256);
+  double* partial = (double*)ws;
+  double* Bm = (double*)((char*)ws + partial_bytes);
+  double* AB = (double*)((char*)ws + partial_bytes + mat_bytes);
+  for (int j0 = 0; j0 < n_odes; j0 += ch) {
+    const int n = min(ch, n_odes - j0);
+    VGM_TRY(program_param_B(prog, X, ld, T, n, ode_class + j0, ode_idx + (size_t)j0 * prog->arity, Bm, s));
+    vgm_gemm_args g;                              // AB[r][t] = sum_s Bm[r][s] A[t][s] = (A B_r)(t)
+    memset(&g, 0, sizeof(g));
+    g.A = Bm; g.B = A; g.C = AB;
+    g.lda = g.ldb = g.ldc = ld;
+    g.N = n * p; g.M = T; g.K = T;
+    g.alpha = 1.0;
+    VGM_TRY(dgemm_nt(g, s));
+    cov_partial_kernel<<<ceil_div(n, COV_ROWS), 256, 0, s>>>(Bm, AB, ld, T, n, p,
+                                                           partial + (size_t)(j0 / COV_ROWS) * p * p);
+    VGM_LAUNCH_OK();
+  }
+  cov_reduce_kernel<<<1, 256, 0, s>>>(partial, ceil_div(n_odes, COV_ROWS), p * p, cov);
   VGM_LAUNCH_OK();
   return VGM_OK;
 }

@@ -74,6 +74,32 @@ VGM_PROG(param_stats)(const double* __restrict__ X, const double* __restrict__ D
   }
 }
 
+// P2 covariance helper: the rows B_{k,i}(t) of the parameter linearisation (proxies...py:66-71) written out for
+// the opt-in parameter covariance  sum_k B_k^T A B_k  (:79).  ODE row j -> rows j*p .. j*p+p-1 of Bout; the padding
+// columns t >= T are zeroed.
+extern "C" __global__ void __launch_bounds__(VGM_PROG_THREADS)
+VGM_PROG(param_B)(const double* __restrict__ X, int ld, int T, int n_rows, const int* __restrict__ ode_class,
+                  const int* __restrict__ ode_idx, double* __restrict__ Bout) {
+  const int j = blockIdx.x;
+  if (j >= n_rows) return;
+  const int cls = ode_class[j];
+  const double* xr[VGM_ARITY];
+#pragma unroll
+  for (int a = 0; a < VGM_ARITY; ++a) xr[a] = X + (size_t)ode_idx[(size_t)j * VGM_ARITY + a] * ld;
+  for (int t = threadIdx.x; t < ld; t += blockDim.x) {
+    double s[VGM_ARITY], B[VGM_NPARAM], b;
+#pragma unroll
+    for (int i = 0; i < VGM_NPARAM; ++i) B[i] = 0.0;
+    if (t < T) {
+#pragma unroll
+      for (int a = 0; a < VGM_ARITY; ++a) s[a] = xr[a][t];
+      vgm_theta_coeffs(cls, s, B, b);
+    }
+#pragma unroll
+    for (int i = 0; i < VGM_NPARAM; ++i) Bout[((size_t)j * VGM_NPARAM + i) * ld + t] = B[i];
+  }
+}
+
 // P4 (snapshot part): per hidden slot i (state u) and time t   (proxies...py:208-232)
 //   Lambda = sum_{k != u} R_uk^2
 //   rhs    = - sum_{k != u} R_uk (r_uk - D x_k)    with D x_k from the sweep-start snapshot;

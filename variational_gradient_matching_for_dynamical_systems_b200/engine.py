@@ -516,6 +516,20 @@ class VGMEngine:
         return self.last_info
 
     # ---- opt-in covariance (P5) -------------------------------------------------------------------
+    def param_cov(self):
+        """p x p matrix sum_k B_k^T A B_k of the parameter update (proxies...py:79; the reference computes it and
+        drops it).  Evaluated on the current states."""
+        if self.ops.A is None:
+            raise ValueError("eps_cov (A) was not given")
+        n_odes = self.problem.n_stats_odes
+        n = self.lib.vgm_param_cov_ws_bytes(n_odes, self.ld, self.p)
+        ws = torch.empty(n + 256, dtype=torch.uint8, device=self.dev)
+        cov = torch.zeros(self.p * self.p, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.vgm_param_cov(self.program.handle, self.X.data_ptr(), self.ops.A.data_ptr(), self.ld, self.T,
+                                          n_odes, self._mt.ode_class, self._mt.ode_idx, cov.data_ptr(), ws.data_ptr(), n,
+                                          _lib.stream_ptr()))
+        return cov.cpu().numpy().reshape(self.p, self.p)
+
     def state_cov(self, state_index, theta_star=None):
         """T x T matrix sum_k B_uk^T A B_uk of one hidden state (proxies...py:239)."""
         if self.ops.A is None:

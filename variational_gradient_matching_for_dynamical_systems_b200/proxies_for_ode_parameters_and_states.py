@@ -115,6 +115,16 @@ def proxy_for_ode_parameters(state_proxy, locally_linear_odes, dC_times_inv_C, e
         'ODE parameter symbols')
 
 
+def covariance_for_ode_parameters(state_proxy, locally_linear_odes, dC_times_inv_C, eps_cov):
+    """Opt-in (not in the reference's surface): the p x p matrix ``sum_k B_k^T A B_k`` that
+    ``proxy_for_ode_parameters`` computes as ``global_cov`` (proxies...py:79) and never returns."""
+    model = _model_of(locally_linear_odes)
+    ops = Operators(dC_times_inv_C, eps_cov)
+    eng = VGMEngine(model, ops, None, hidden=(), couplings=None, theta_mode="proxy")
+    eng.set_states(np.asarray(state_proxy.values, dtype=np.float64))
+    return eng.param_cov()
+
+
 def proxy_for_ind_states(state_proxy, ode_param_proxy, odes, odes_gradient_states, locally_linear_odes,
                          dC_times_inv_C, eps_cov, state_pred_mean, state_pred_inv_cov, observations, true_states,
                          state_couplings, burnin=5, clamp_states_to_observation_fit=True, constraints=None,
