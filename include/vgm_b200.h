@@ -47,9 +47,23 @@ int vgm_version(void);
  * C_obs on t2 (T2 x T2, ld2) and C_state_obs (T x T2, ld2).  Any output pointer may be null.
  * kernel_type: VGM_KERNEL_RBF  param_host = [lengthscale, sigma]         (GP_regression.py:176-179)
  *              VGM_KERNEL_RQ   param_host = [alpha, lengthscale, sigma]  (GP_regression.py:205-209)
- * The result is scaled by sigma^2 = param[-1]^2 (GP_regression.py:232).
+ *              VGM_KERNEL_PERIODIC         reads param[0], param[1]       (:181-184)
+ *              VGM_KERNEL_LOCALLY_PERIODIC reads param[1], param[2]       (:185-188)
+ *              VGM_KERNEL_RBF_LIN          reads param[1..4]              (:189-192)
+ *              VGM_KERNEL_SIGMOID          reads param[1], param[2]       (:193-195)
+ *              VGM_KERNEL_SIGMOID2         reads param[0], param[1]       (:196-198)
+ *              VGM_KERNEL_EXP_SIN_SQUARED  reads param[0], param[1]       (:199-204)
+ *              VGM_KERNEL_MATERN           param = [lengthscale, nu, ...], nu in {0.5, 1.5, 2.5} (:210-223; the
+ *                                          reference's general-nu branch cannot run)
+ * The result is scaled by sigma^2 = param[-1]^2 (GP_regression.py:232).  The three types built on
+ * sqrt((t0-t1)^2) (periodic, locally periodic, exp_sin_squared) have NaN derivative grids on t0 == t1, exactly
+ * as the reference's lambdified derivatives do.
  */
-enum { VGM_KERNEL_RBF = 0, VGM_KERNEL_RQ = 1 };
+enum {
+  VGM_KERNEL_RBF = 0, VGM_KERNEL_RQ = 1, VGM_KERNEL_PERIODIC = 2, VGM_KERNEL_LOCALLY_PERIODIC = 3,
+  VGM_KERNEL_RBF_LIN = 4, VGM_KERNEL_SIGMOID = 5, VGM_KERNEL_SIGMOID2 = 6, VGM_KERNEL_EXP_SIN_SQUARED = 7,
+  VGM_KERNEL_MATERN = 8
+};
 int vgm_kernel_build(int kernel_type, const double* param_host, int n_param,
                      const double* t, int T, const double* t2, int T2, int ld, int ld2,
                      double* C, double* dC, double* ddC, double* Cobs, double* Cso,
@@ -119,6 +133,12 @@ int vgm_transpose(const double* in, int ld_in, double* out, int ld_out, int rows
 size_t vgm_gm_operators_ws_bytes(int T, int ld);
 int vgm_gm_operators(const double* C, const double* dC, const double* ddC, int T, int ld, int batch,
                      double* D, double* A, double* Cinv, void* ws, size_t ws_bytes, vgm_stream_t stream);
+/* Same operators through LU with partial pivoting (the reference's own route, np.linalg.solve at :306) for a C
+ * that is not positive definite -- the 'sigmoid2' kernel and the reference's Matern 1.5 / 2.5 on the squared
+ * distance are indefinite.  One CTA factorises; use it when vgm_gm_operators returns VGM_ENOTSPD.  Same workspace
+ * size.  Returns VGM_ENOTSPD if a column has no non-zero pivot. */
+int vgm_gm_operators_lu(const double* C, const double* dC, const double* ddC, int T, int ld, double* D, double* A,
+                        void* ws, size_t ws_bytes, vgm_stream_t stream);
 int vgm_spd_inverse(const double* S, int T, int ld, double* Sinv, void* ws, size_t ws_bytes, vgm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

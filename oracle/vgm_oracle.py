@@ -67,8 +67,17 @@ def _kernel_sympy(kernel_type, kernel_param):
     if kernel_type == "periodic":
         dist = (t0 - t1) / p[1]
         k = sym.exp(-2 * sym.sin(np.pi * sym.sqrt(dist ** 2) / p[1]) ** 2 / p[0] ** 2)
+    elif kernel_type == "locally_periodic":
+        dist = t0 - t1
+        k = sym.exp(-dist ** 2 / 2 * p[1] ** 2) * sym.exp(
+            -2 * sym.sin(np.pi * sym.sqrt((t0 - t1) ** 2) / p[2]) ** 2 / p[1] ** 2)
     elif kernel_type == "rbf+lin":
         k = sym.exp(-(t0 - t1) ** 2 / p[1] ** 2) + p[2] + p[3] * (t0 - p[4]) * (t1 - p[4])
+    elif kernel_type == "sigmoid":
+        k = sym.asin((p[1] + p[2] * t0 * t1) / sym.sqrt((p[1] + p[2] * t0 ** 2 + 1) * (p[1] + p[2] * t1 ** 2 + 1)))
+    elif kernel_type == "exp_sin_squared":
+        dist = sym.sqrt((t0 - t1) ** 2)
+        k = sym.exp(-2 * (sym.sin(np.pi * dist / p[1]) / p[0]) ** 2)
     elif kernel_type == "sigmoid2":
         k = sym.tanh(p[0] * t0 * t1 + p[1])
     elif kernel_type == "matern" and p[1] in (0.5, 1.5, 2.5):

@@ -292,6 +292,93 @@ def test_kernel_function_T1000_vs_oracle(pkg):
     assert relerr(out["A"], A) < TOL * 1e-2
 
 
+def _nan_relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(b)
+    return relerr(a[m], b[m])
+
+
+@pytest.mark.parametrize("case", ["matern05_T24", "matern15_T24", "matern25_T24", "rbf_lin_T20", "sigmoid_T8",
+                                  "sigmoid2_T8"])
+def test_kernel_function_other_types_vs_reference_golden(pkg, case):
+    """Kernel types beyond rbf / RQ (GP_regression.py:181-231): grids against the oracle's symbolic derivatives, the
+    drop-in kernel_function against the live reference's outputs.  Matern 1.5 / 2.5 (written on the squared distance
+    there) and sigmoid2 are indefinite: Cholesky reports it and the LU route takes over."""
+    from variational_gradient_matching_for_dynamical_systems_b200 import GP_regression as gpr
+    g = load("kernel_function_types.npz")
+    t, t2, ktype, kparam = g[case + "__t"], g[case + "__t2"], str(g[case + "__type"]), list(g[case + "__param"])
+    o = gpr.kernel_function_device(t, t2, ktype, kparam)
+    T, T2 = len(t), len(t2)
+    Cm, dC, ddC, Cobs, Cso = vo.kernel_matrices(t, t2, ktype, kparam)
+    for k, v, r, c in (("C", Cm, T, T), ("dC", dC, T, T), ("ddC", ddC, T, T), ("Cobs", Cobs, T2, T2), ("Cso", Cso, T, T2)):
+        assert relerr(o[k][:r, :c].cpu().numpy(), v) < 1e-12, k
+    indefinite = np.linalg.eigvalsh(g[case + "__C"])[0] < 0
+    assert (o.get("factorisation") == "lu") == indefinite
+    D, A, Cc, Cobs2, Cso2 = gpr.kernel_function(t, t2, ktype, kparam)
+    tol = max(1e-11, 50 * float(g[case + "__condC"]) * 2.2e-16)       # the solve's error bound, cond(C) * eps
+    assert relerr(Cc, g[case + "__C"]) < 1e-13
+    assert relerr(Cobs2, g[case + "__Cobs"]) < 1e-13
+    assert relerr(Cso2, g[case + "__Cso"]) < 1e-13
+    assert relerr(D, g[case + "__D"]) < tol
+    assert relerr(A, g[case + "__A"]) < tol
+
+
+@pytest.mark.parametrize("ktype,kparam", [("periodic", [0.8, 1.7, 1.1]), ("locally_periodic", [0.0, 0.9, 2.3, 1.2]),
+                                          ("exp_sin_squared", [0.7, 2.9, 0.8])])
+def test_kernel_types_on_sqrt_of_squared_distance(pkg, ktype, kparam):
+    """sqrt((t0-t1)**2) has no derivative at t0 == t1: the reference's lambdified derivative grids are NaN on the
+    diagonal and its kernel_function raises LinAlgError (from the plot-only draw at :310-311).  Grids (with the same
+    NaN pattern) against the oracle's symbolic route; the drop-in raises like the reference."""
+    from variational_gradient_matching_for_dynamical_systems_b200 import GP_regression as gpr
+    p, _lib, _ = pkg
+    lib = _lib.load()
+    t, t2 = np.arange(16) * 0.21, np.array([0.1, 0.5, 1.9])
+    with np.errstate(all="ignore"):
+        Cm, dC, ddC, Cobs, Cso = vo.kernel_matrices(t, t2, ktype, kparam)
+    assert np.isnan(np.diag(dC)).all() and not np.isnan(Cm).any()
+    T, T2, ld = 16, 3, 16
+    td, t2d = torch.as_tensor(t, device="cuda"), torch.as_tensor(t2, device="cuda")
+    z = lambda r, l: torch.zeros((r, l), dtype=torch.float64, device="cuda")
+    gC, gdC, gddC, gCobs, gCso = z(T, ld), z(T, ld), z(T, ld), z(T2, 8), z(T, 8)
+    par = (C.c_double * len(kparam))(*kparam)
+    _lib.check(lib.vgm_kernel_build(gpr._KTYPES[ktype], par, len(kparam), td.data_ptr(), T, t2d.data_ptr(), T2, ld, 8,
+                                    gC.data_ptr(), gdC.data_ptr(), gddC.data_ptr(), gCobs.data_ptr(), gCso.data_ptr(),
+                                    _lib.stream_ptr()))
+    assert relerr(gC[:, :T].cpu().numpy(), Cm) < 1e-12
+    assert relerr(gCobs[:, :T2].cpu().numpy(), Cobs) < 1e-12
+    assert relerr(gCso[:, :T2].cpu().numpy(), Cso) < 1e-12
+    assert _nan_relerr(gdC[:, :T].cpu().numpy(), dC) < 1e-12
+    assert _nan_relerr(gddC[:, :T].cpu().numpy(), ddC) < 1e-12
+    with pytest.raises(np.linalg.LinAlgError):
+        gpr.kernel_function(t, t2, ktype, kparam)
+
+
+def test_kernel_function_errors_like_the_reference(pkg):
+    from variational_gradient_matching_for_dynamical_systems_b200 import GP_regression as gpr
+    t = np.arange(8) * 0.1
+    with pytest.raises(UnboundLocalError):                      # GP_regression.py:232 on an unknown kernel_type
+        gpr.kernel_function(t, t, "no_such_kernel", [1.0, 1.0])
+    with pytest.raises(NotImplementedError):                    # general-nu Matern cannot run in the reference either
+        gpr.kernel_function(t, t, "matern", [1.0, 0.7, 1.0])
+    with pytest.raises(ValueError):
+        gpr.kernel_function(list(t), t, "rbf", [1.0, 1.0])
+
+
+def test_lu_route_T1000_indefinite_matern_vs_oracle(pkg):
+    """The single-CTA LU at full size: Matern 1.5 on the squared distance, T = 1000, cond(C) ~ 3e4, min eig < 0."""
+    from variational_gradient_matching_for_dynamical_systems_b200 import GP_regression as gpr
+    t = np.arange(1000) * 0.05
+    kp = [0.06, 1.5, 1.0]
+    o = gpr.kernel_function_device(t, t[:4], "matern", kp)
+    assert o["factorisation"] == "lu"
+    Cm, dC, ddC, _, _ = vo.kernel_matrices(t, t[:4], "matern", kp)
+    D, A = vo.gm_operators(Cm, dC, ddC)
+    assert relerr(o["dC"][:, :1000].cpu().numpy(), dC) < 1e-12
+    assert relerr(o["D"][:, :1000].cpu().numpy(), D) < TOL
+    assert relerr(o["A"][:, :1000].cpu().numpy(), A) < TOL
+
+
 def test_cholesky_reports_non_spd(pkg):
     _, _lib, _ = pkg
     lib = _lib.load()

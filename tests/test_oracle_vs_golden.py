@@ -36,6 +36,23 @@ def test_kernel_function_matches_reference(case):
     assert relerr(A, g[case + "__A"]) < tol
 
 
+OTHER_TYPES = ["matern05_T24", "matern15_T24", "matern25_T24", "rbf_lin_T20", "sigmoid_T8", "sigmoid2_T8"]
+
+
+@pytest.mark.parametrize("case", OTHER_TYPES)
+def test_kernel_function_other_types_match_reference(case):
+    """Kernel types beyond rbf / RQ (GP_regression.py:181-231), golden from oracle/make_golden_kernel_types.py."""
+    g = load("kernel_function_types.npz")
+    t, t2 = g[case + "__t"], g[case + "__t2"]
+    D, A, C, Cobs, Cso = vo.kernel_function(t, t2, str(g[case + "__type"]), list(g[case + "__param"]))
+    assert relerr(C, g[case + "__C"]) < 1e-14
+    assert relerr(Cobs, g[case + "__Cobs"]) < 1e-14
+    assert relerr(Cso, g[case + "__Cso"]) < 1e-14
+    tol = max(1e-12, 50 * float(g[case + "__condC"]) * 2.2e-16)
+    assert relerr(D, g[case + "__D"]) < tol
+    assert relerr(A, g[case + "__A"]) < tol
+
+
 def test_kernel_function_default_rq_grids_only():
     # reference default RQ [0.1,2,5] on the Lotka-Volterra grid: cond(C) ~ 1e17, so only the
     # kernel grids (not the solve) are comparable

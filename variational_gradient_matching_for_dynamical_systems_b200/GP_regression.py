@@ -18,7 +18,11 @@ import torch
 
 from . import _lib
 
-_KTYPES = {"rbf": _lib.KERNEL_RBF, "RQ": _lib.KERNEL_RQ}
+# kernel_type strings of GP_regression.py:176-231
+_KTYPES = {"rbf": _lib.KERNEL_RBF, "RQ": _lib.KERNEL_RQ, "periodic": _lib.KERNEL_PERIODIC,
+           "locally_periodic": _lib.KERNEL_LOCALLY_PERIODIC, "rbf+lin": _lib.KERNEL_RBF_LIN,
+           "sigmoid": _lib.KERNEL_SIGMOID, "sigmoid2": _lib.KERNEL_SIGMOID2,
+           "exp_sin_squared": _lib.KERNEL_EXP_SIN_SQUARED, "matern": _lib.KERNEL_MATERN}
 
 
 def _round_up(x, m):
@@ -31,9 +35,12 @@ def kernel_function_device(time_points, time_points2, kernel_type="RQ", kernel_p
     ``D, A, C, dC, ddC, Cobs, Cso`` (+ ``Cinv``), each ``[rows, ld]`` with ``ld`` = columns
     rounded up to 8, plus ``T``/``T2``."""
     if kernel_type not in _KTYPES:
-        raise NotImplementedError(
-            "kernel_type %r: the B200 path implements the closed-form 'rbf' and 'RQ' kernels "
-            "(GP_regression.py:176-179,205-209)" % (kernel_type,))
+        # the reference falls through its if/elif chain and fails on the unassigned name at :232
+        raise UnboundLocalError("cannot access local variable 'kernel' where it is not associated with a value "
+                                "(unknown kernel_type %r)" % (kernel_type,))
+    if kernel_type == "matern" and float(kernel_param[1]) not in (0.5, 1.5, 2.5):
+        raise NotImplementedError("matern with nu=%r: the reference's general-nu branch (GP_regression.py:224-230) "
+                                  "indexes a SymPy expression and cannot run" % (kernel_param[1],))
     lib = _lib.load()
     dev = _lib.require_cuda()
     t = torch.as_tensor(np.asarray(time_points, dtype=np.float64), device=dev)
@@ -51,8 +58,15 @@ def kernel_function_device(time_points, time_points2, kernel_type="RQ", kernel_p
     n = lib.vgm_gm_operators_ws_bytes(T, ld)
     ws = torch.empty(n, dtype=torch.uint8, device=dev)
     cinv = z(T, ld) if want_inverse else None
-    _lib.check(lib.vgm_gm_operators(out["C"].data_ptr(), out["dC"].data_ptr(), out["ddC"].data_ptr(), T, ld, 1,
-                                    out["D"].data_ptr(), out["A"].data_ptr(), _lib.ptr(cinv), ws.data_ptr(), n, s))
+    rc = lib.vgm_gm_operators(out["C"].data_ptr(), out["dC"].data_ptr(), out["ddC"].data_ptr(), T, ld, 1,
+                              out["D"].data_ptr(), out["A"].data_ptr(), _lib.ptr(cinv), ws.data_ptr(), n, s)
+    if rc == _lib.VGM_ENOTSPD and not want_inverse:
+        # indefinite C ('sigmoid2', the reference's Matern 1.5/2.5 on the squared distance): LU with partial
+        # pivoting, which is what the reference's np.linalg.solve does for every kernel (GP_regression.py:306)
+        rc = lib.vgm_gm_operators_lu(out["C"].data_ptr(), out["dC"].data_ptr(), out["ddC"].data_ptr(), T, ld,
+                                     out["D"].data_ptr(), out["A"].data_ptr(), ws.data_ptr(), n, s)
+        out["factorisation"] = "lu"
+    _lib.check(rc)
     if want_inverse:
         out["Cinv"] = cinv
     return out
@@ -66,6 +80,10 @@ def kernel_function(time_points, time_points2, kernel_type='RQ', kernel_param=[0
         raise ValueError('time points is not a numpy array')
     elif len(time_points.shape) > 1:
         raise ValueError('time points must be a one dimensional numpy array')
+    if kernel_type in ("periodic", "locally_periodic", "exp_sin_squared"):
+        # sqrt((t0-t1)**2) makes the reference's derivative grids NaN on the diagonal; its plot-only
+        # multivariate_normal draw (:310-311) then fails.  kernel_function_device still builds the grids.
+        raise np.linalg.LinAlgError("SVD did not converge")
     o = kernel_function_device(time_points, np.asarray(time_points2, dtype=float), kernel_type, kernel_param)
     T, T2 = o["T"], o["T2"]
     c = lambda m, r, n: m[:r, :n].cpu().numpy()

@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libvgm_b200.so")
 
 VGM_OK, VGM_EINVAL, VGM_ECUDA, VGM_ENOTCONV, VGM_ENOTSPD, VGM_EDRIVER = 0, -1, -2, -3, -4, -5
 KERNEL_RBF, KERNEL_RQ = 0, 1
+(KERNEL_PERIODIC, KERNEL_LOCALLY_PERIODIC, KERNEL_RBF_LIN, KERNEL_SIGMOID, KERNEL_SIGMOID2, KERNEL_EXP_SIN_SQUARED,
+ KERNEL_MATERN) = range(2, 9)
 
 
 class VGMError(RuntimeError):
@@ -102,6 +104,7 @@ SIGNATURES = {
     "vgm_gm_operators_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vgm_gm_operators": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_size_t,
                                    C.c_void_p]),
+    "vgm_gm_operators_lu": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_size_t, C.c_void_p]),
     "vgm_spd_inverse": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_size_t, C.c_void_p]),
     "vgm_program_builtin": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
     "vgm_program_load": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int, _P(C.c_void_p)]),

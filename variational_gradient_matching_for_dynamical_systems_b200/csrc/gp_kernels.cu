@@ -10,26 +10,119 @@ int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s);
 // K1 kernel_build: one thread per (i, column pair), 16-byte stores.  HBM-write bound.
 // ------------------------------------------------------------------------------------
 struct KernelParams {
-  int type;
-  double p0, p1, sig2;
+  int type, n;
+  double p[6];      // kernel_param[0..5] as given (missing entries 0)
+  double sig2;      // kernel_param[-1]^2                               GP_regression.py:232
 };
 
-__device__ __forceinline__ void eval_kernel(const KernelParams& kp, double d, double& k, double& dk, double& ddk) {
+// Second-order jet in (t0, t1): value, d/dt0, d/dt1, d2/dt0dt1.  The kernel types beyond rbf/RQ are written as the
+// reference writes them (GP_regression.py:181-231) and differentiated by propagation, which is what its
+// kernel.diff(t0).diff(t1) (:236-237) does symbolically.  sqrt((t0-t1)^2) has no derivative at t0 == t1: the
+// reference's lambdified expressions give 0/0 = NaN there and so does the jet (inf * 0).
+struct Jet {
+  double v, a, b, c;
+};
+__device__ __forceinline__ Jet jconst(double x) { return {x, 0.0, 0.0, 0.0}; }
+__device__ __forceinline__ Jet operator+(Jet u, Jet w) { return {u.v + w.v, u.a + w.a, u.b + w.b, u.c + w.c}; }
+__device__ __forceinline__ Jet operator-(Jet u, Jet w) { return {u.v - w.v, u.a - w.a, u.b - w.b, u.c - w.c}; }
+__device__ __forceinline__ Jet operator+(Jet u, double x) { return {u.v + x, u.a, u.b, u.c}; }
+__device__ __forceinline__ Jet operator*(Jet u, double x) { return {u.v * x, u.a * x, u.b * x, u.c * x}; }
+__device__ __forceinline__ Jet operator*(Jet u, Jet w) {
+  return {u.v * w.v, u.a * w.v + u.v * w.a, u.b * w.v + u.v * w.b, u.c * w.v + u.a * w.b + u.b * w.a + u.v * w.c};
+}
+// f(u) with f, f', f'' evaluated at u.v
+__device__ __forceinline__ Jet jfn(Jet u, double f, double f1, double f2) {
+  return {f, f1 * u.a, f1 * u.b, f2 * u.a * u.b + f1 * u.c};
+}
+__device__ __forceinline__ Jet jexp(Jet u) { const double e = exp(u.v); return jfn(u, e, e, e); }
+__device__ __forceinline__ Jet jsin(Jet u) { const double sn = sin(u.v); return jfn(u, sn, cos(u.v), -sn); }
+__device__ __forceinline__ Jet jtanh(Jet u) {
+  const double th = tanh(u.v), f1 = 1.0 - th * th;
+  return jfn(u, th, f1, -2.0 * th * f1);
+}
+__device__ __forceinline__ Jet jasin(Jet u) {
+  const double w = 1.0 - u.v * u.v, f1 = 1.0 / sqrt(w);
+  return jfn(u, asin(u.v), f1, u.v * f1 / w);
+}
+__device__ __forceinline__ Jet jsqrt(Jet u) {
+  const double r = sqrt(u.v);
+  return jfn(u, r, 0.5 / r, -0.25 / (r * u.v));
+}
+__device__ __forceinline__ Jet jrecip(Jet u) {
+  const double f = 1.0 / u.v;
+  return jfn(u, f, -f * f, 2.0 * f * f * f);
+}
+
+__device__ __forceinline__ Jet eval_kernel_jet(const KernelParams& kp, double t0v, double t1v) {
+  const double PI = 3.141592653589793;
+  const Jet t0 = {t0v, 1.0, 0.0, 0.0}, t1 = {t1v, 0.0, 1.0, 0.0};
+  const Jet d = t0 - t1;
+  const double* p = kp.p;
+  Jet k;
+  switch (kp.type) {
+    case VGM_KERNEL_PERIODIC: {            // :181-184  exp(-2 sin(pi sqrt(dist^2) / p1)^2 / p0^2), dist = d / p1
+      const Jet dist = d * (1.0 / p[1]);
+      const Jet sn = jsin(jsqrt(dist * dist) * (PI / p[1]));
+      k = jexp(sn * sn * (-2.0 / (p[0] * p[0])));
+    } break;
+    case VGM_KERNEL_LOCALLY_PERIODIC: {    // :185-188  exp(-d^2 / 2 * p1^2) exp(-2 sin(pi sqrt(d^2) / p2)^2 / p1^2)
+      const Jet sn = jsin(jsqrt(d * d) * (PI / p[2]));
+      k = jexp(d * d * (-0.5 * p[1] * p[1])) * jexp(sn * sn * (-2.0 / (p[1] * p[1])));
+    } break;
+    case VGM_KERNEL_RBF_LIN: {             // :189-192  exp(-d^2 / p1^2) + p2 + p3 (t0 - p4)(t1 - p4)
+      k = jexp(d * d * (-1.0 / (p[1] * p[1]))) + (t0 + (-p[4])) * (t1 + (-p[4])) * p[3] + p[2];
+    } break;
+    case VGM_KERNEL_SIGMOID: {             // :193-195  asin((p1 + p2 t0 t1) / sqrt((p1 + p2 t0^2 + 1)(p1 + p2 t1^2 + 1)))
+      const Jet num = t0 * t1 * p[2] + p[1];
+      const Jet den = (t0 * t0 * p[2] + (p[1] + 1.0)) * (t1 * t1 * p[2] + (p[1] + 1.0));
+      k = jasin(num * jrecip(jsqrt(den)));
+    } break;
+    case VGM_KERNEL_SIGMOID2: {            // :196-198  tanh(p0 t0 t1 + p1)
+      k = jtanh(t0 * t1 * p[0] + p[1]);
+    } break;
+    case VGM_KERNEL_EXP_SIN_SQUARED: {     // :199-204  exp(-2 (sin(pi sqrt(d^2) / p1) / p0)^2)
+      const Jet sn = jsin(jsqrt(d * d) * (PI / p[1])) * (1.0 / p[0]);
+      k = jexp(sn * sn * (-2.0));
+    } break;
+    default: {                             // VGM_KERNEL_MATERN :210-223, dist = (d / p0)^2 (squared, as written there)
+      const Jet dist = d * d * (1.0 / (p[0] * p[0]));
+      if (p[1] == 0.5) {
+        k = jexp(dist * (-1.0));
+      } else if (p[1] == 1.5) {
+        const Jet kk = dist * sqrt(3.0);
+        k = (kk + 1.0) * jexp(kk * (-1.0));
+      } else {
+        const Jet kk = dist * sqrt(5.0);
+        k = (kk + kk * kk * (1.0 / 3.0) + 1.0) * jexp(kk * (-1.0));
+      }
+    } break;
+  }
+  return k * kp.sig2;
+}
+
+__device__ __forceinline__ void eval_kernel(const KernelParams& kp, double t0, double t1, double& k, double& dk,
+                                            double& ddk) {
+  const double d = t0 - t1;
   if (kp.type == VGM_KERNEL_RBF) {
     // k = s^2 exp(-d^2 / (2 l^2))                                  GP_regression.py:176-179
-    const double il2 = 1.0 / (kp.p0 * kp.p0);
+    const double il2 = 1.0 / (kp.p[0] * kp.p[0]);
     k = kp.sig2 * exp(-0.5 * d * d * il2);
     dk = -d * il2 * k;
     ddk = (il2 - d * d * il2 * il2) * k;
-  } else {
+  } else if (kp.type == VGM_KERNEL_RQ) {
     // k = s^2 (1 + d^2 / (2 a l^2))^-a                             GP_regression.py:205-209
-    const double al = kp.p0, il2 = 1.0 / (kp.p1 * kp.p1);
+    const double al = kp.p[0], il2 = 1.0 / (kp.p[1] * kp.p[1]);
     const double base = 1.0 + d * d * il2 / (2.0 * al);
     const double lb = log(base);
     const double pa1 = exp(-(al + 1.0) * lb);   // base^-(a+1)
     k = kp.sig2 * pa1 * base;
     dk = -kp.sig2 * d * il2 * pa1;
     ddk = kp.sig2 * il2 * pa1 - kp.sig2 * d * d * il2 * il2 * (al + 1.0) / al * pa1 / base;
+  } else {
+    const Jet j = eval_kernel_jet(kp, t0, t1);
+    k = j.v;
+    dk = j.a;
+    ddk = j.c;
   }
 }
 
@@ -41,9 +134,9 @@ __global__ void kernel_build_kernel(KernelParams kp, const double* __restrict__ 
   if (j >= Tb) return;
   const double ti = ta[i];
   double k0, dk0, ddk0, k1 = 0, dk1 = 0, ddk1 = 0;
-  eval_kernel(kp, ti - tb[j], k0, dk0, ddk0);
+  eval_kernel(kp, ti, tb[j], k0, dk0, ddk0);
   const bool two = (j + 1 < Tb);
-  if (two) eval_kernel(kp, ti - tb[j + 1], k1, dk1, ddk1);
+  if (two) eval_kernel(kp, ti, tb[j + 1], k1, dk1, ddk1);
   const size_t o = (size_t)i * ld + j;
   if (two || (j + 1 < ld)) {   // ld is even, so the pad slot exists: keep it zero
     if (C) *reinterpret_cast<double2*>(C + o) = make_double2(k0, k1);
@@ -206,9 +299,12 @@ static int potrf(double* S, int ld, int T, int* bad_pivot, cudaStream_t s) {
   return VGM_OK;
 }
 
-// R <- R L^-T L^-1  (= R S^-1), R is [n_rows x T] row-major, in place.  LT = L^T.
-static int chol_solve_right(const double* L, const double* LT, int ld, int T, double* R, int ldr, int n_rows,
-                            cudaStream_t s) {
+// R <- R F1^-T F2^-1, R is [n_rows x T] row-major, in place; F1, F2 lower triangular, F2T = F2^T.
+//   Cholesky S = L L^T:        F1 = F2 = L        ->  R S^-1
+//   LU       P S = Lu U:       F1 = U^T, F2 = Lu  ->  R U^-1 Lu^-1  (the column permutation is applied by the caller)
+static int tri_solve_right(const double* F1, const double* F2, const double* F2T, int ld, int T, double* R, int ldr,
+                           int n_rows, cudaStream_t s) {
+  const double *L = F1, *LT = F2T;
   // W L^T = R : column blocks ascending;  W[:,j] = (R[:,j] - sum_{k<j} W[:,k] L[j,k]^T) L_jj^-T
   for (int j0 = 0; j0 < T; j0 += NB) {
     const int nb = min(NB, T - j0);
@@ -239,19 +335,113 @@ static int chol_solve_right(const double* L, const double* LT, int ld, int T, do
       g.alpha = -1.0; g.beta = 1.0;
       VGM_TRY(dgemm_nt(g, s));
     }
-    trsm_diag_rows_kernel<<<ceil_div(n_rows, 128), 128, 0, s>>>(L, ld, j0, nb, R, ldr, n_rows, 1);
+    trsm_diag_rows_kernel<<<ceil_div(n_rows, 128), 128, 0, s>>>(F2, ld, j0, nb, R, ldr, n_rows, 1);
     VGM_LAUNCH_OK();
   }
   return VGM_OK;
+}
+
+static int chol_solve_right(const double* L, const double* LT, int ld, int T, double* R, int ldr, int n_rows,
+                            cudaStream_t s) {
+  return tri_solve_right(L, L, LT, ld, T, R, ldr, n_rows, s);
+}
+
+// ------------------------------------------------------------------------------------
+// LU with partial pivoting (what the reference's np.linalg.solve / LAPACK gesv does, GP_regression.py:306) for
+// covariance matrices that are not positive definite: the tanh "sigmoid2" kernel and the reference's Matern
+// 1.5 / 2.5 written on the SQUARED distance (:212-223) are indefinite.  One CTA, right-looking, rank-1 updates
+// out of L2: O(T^3 / 3) on one SM is tens of milliseconds at T = 1000, a one-time set-up cost for rare kernels.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) lu_single_cta_kernel(double* __restrict__ Am, int ld, int T,
+                                                             int* __restrict__ perm, int* __restrict__ flag) {
+  __shared__ double red_v[32];
+  __shared__ int red_i[32];
+  __shared__ int s_piv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int i = tid; i < T; i += blockDim.x) perm[i] = i;
+  __syncthreads();
+  for (int k = 0; k < T; ++k) {
+    // pivot: first row of maximal |a[r][k]|, r >= k (LAPACK idamax)
+    double bv = -1.0;
+    int bi = k;
+    for (int r = k + tid; r < T; r += blockDim.x) {
+      const double v = fabs(Am[(size_t)r * ld + k]);
+      if (v > bv) { bv = v; bi = r; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = lane < nw ? red_v[lane] : -1.0;
+      bi = lane < nw ? red_i[lane] : T;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        s_piv = bi;
+        if (!(bv > 0.0)) atomicCAS(flag, 0, k + 1);        // exactly singular (or NaN) column
+        const int t = perm[k]; perm[k] = perm[bi]; perm[bi] = t;
+      }
+    }
+    __syncthreads();
+    const int p = s_piv;
+    if (p != k)
+      for (int c = tid; c < T; c += blockDim.x) {
+        const double a = Am[(size_t)k * ld + c], b = Am[(size_t)p * ld + c];
+        Am[(size_t)k * ld + c] = b;
+        Am[(size_t)p * ld + c] = a;
+      }
+    __syncthreads();
+    const double inv = 1.0 / Am[(size_t)k * ld + k];
+    const double* rowk = Am + (size_t)k * ld;
+    for (int r = k + 1 + warp; r < T; r += nw) {
+      double* rowr = Am + (size_t)r * ld;
+      const double l = rowr[k] * inv;
+      for (int c = k + 1 + lane; c < T; c += 32) rowr[c] -= l * rowk[c];
+      __syncwarp();
+      if (lane == 0) rowr[k] = l;
+    }
+    __syncthreads();
+  }
+}
+
+// LUm (packed) -> Lu (unit lower, explicit ones), UT = U^T (lower)
+__global__ void lu_unpack_kernel(const double* __restrict__ LUm, int ld, int T, double* __restrict__ Lu,
+                                 double* __restrict__ UT) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= ld) return;
+  const bool in = c < T;
+  Lu[(size_t)r * ld + c] = !in ? 0.0 : (c < r ? LUm[(size_t)r * ld + c] : (c == r ? 1.0 : 0.0));
+  UT[(size_t)r * ld + c] = (in && c <= r) ? LUm[(size_t)c * ld + r] : 0.0;
+}
+
+// D[row][perm[i]] = V[row][i]
+__global__ void permute_cols_kernel(const double* __restrict__ V, int ldv, double* __restrict__ Dm, int ldd, int T,
+                                    const int* __restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+  if (i < T) Dm[(size_t)row * ldd + perm[i]] = V[(size_t)row * ldv + i];
 }
 
 struct CholWs {
   double* L;
   double* LT;
   int* flag;
+  double* extra;   // 3 more matrices (LU route)
+  int* perm;
 };
 
-static size_t chol_ws_bytes(int T, int ld) { return 2 * align_up((size_t)T * ld * sizeof(double), 256) + 256; }
+// 2 matrices for the Cholesky route; the LU route (vgm_gm_operators_lu) needs 5 plus the permutation
+static size_t chol_ws_bytes(int T, int ld) {
+  return 5 * align_up((size_t)T * ld * sizeof(double), 256) + align_up((size_t)T * sizeof(int), 256) + 256;
+}
 
 static int chol_ws_carve(void* ws, size_t ws_bytes, int T, int ld, CholWs& w) {
   VGM_REQUIRE(ws && ws_bytes >= chol_ws_bytes(T, ld), "workspace too small");
@@ -260,7 +450,9 @@ static int chol_ws_carve(void* ws, size_t ws_bytes, int T, int ld, CholWs& w) {
   const size_t mat = align_up((size_t)T * ld * sizeof(double), 256);
   w.L = (double*)p;
   w.LT = (double*)(p + mat);
-  w.flag = (int*)(p + 2 * mat);
+  w.flag = (int*)(p + 5 * mat);
+  w.extra = (double*)(p + 2 * mat);
+  w.perm = (int*)(p + 5 * mat + 256);
   return VGM_OK;
 }
 
@@ -291,13 +483,21 @@ extern "C" int vgm_kernel_build(int kernel_type, const double* param_host, int n
                                 const double* t2, int T2, int ld, int ld2, double* C, double* dC, double* ddC,
                                 double* Cobs, double* Cso, vgm_stream_t stream) {
   VGM_REQUIRE(param_host && n_param >= 2, "kernel parameters");
-  VGM_REQUIRE(kernel_type == VGM_KERNEL_RBF || kernel_type == VGM_KERNEL_RQ, "kernel_type");
-  VGM_REQUIRE(kernel_type != VGM_KERNEL_RQ || n_param >= 3, "RQ needs [alpha, lengthscale, sigma]");
+  VGM_REQUIRE(kernel_type >= VGM_KERNEL_RBF && kernel_type <= VGM_KERNEL_MATERN, "kernel_type");
+  static const int need[] = {2, 3, 2, 3, 5, 3, 2, 2, 2};   // entries of kernel_param each type reads (see vgm_b200.h)
+  if (n_param < need[kernel_type]) {
+    set_error("kernel type %d reads %d entries of kernel_param, %d given", kernel_type, need[kernel_type], n_param);
+    return VGM_EINVAL;
+  }
+  if (kernel_type == VGM_KERNEL_MATERN && param_host[1] != 0.5 && param_host[1] != 1.5 && param_host[1] != 2.5) {
+    set_error("matern: nu = %g; only 0.5, 1.5, 2.5 evaluate in the reference (GP_regression.py:215-223)", param_host[1]);
+    return VGM_EINVAL;
+  }
   VGM_REQUIRE(T >= 0 && T2 >= 0 && (ld % 2) == 0 && (ld2 % 2) == 0 && ld >= T && ld2 >= T2, "shape");
   KernelParams kp;
   kp.type = kernel_type;
-  kp.p0 = param_host[0];
-  kp.p1 = param_host[1];
+  kp.n = n_param;
+  for (int i = 0; i < 6; ++i) kp.p[i] = i < n_param ? param_host[i] : 0.0;
   kp.sig2 = param_host[n_param - 1] * param_host[n_param - 1];
   cudaStream_t s = (cudaStream_t)stream;
   if (T > 0) VGM_TRY(kernel_build_one(kp, t, T, t, T, ld, C, dC, ddC, s));
@@ -348,6 +548,48 @@ extern "C" int vgm_gm_operators(const double* C, const double* dC, const double*
       VGM_TRY(chol_solve_right(w.L, w.LT, ld, T, Ib, ld, T, s));
     }
     VGM_TRY(check_pivot(w, s));
+  }
+  return VGM_OK;
+}
+
+extern "C" int vgm_gm_operators_lu(const double* C, const double* dC, const double* ddC, int T, int ld, double* D,
+                                   double* A, void* ws, size_t ws_bytes, vgm_stream_t stream) {
+  VGM_REQUIRE(C && dC && D && T > 0 && (ld % 2) == 0 && ld >= T, "gm_operators_lu arguments");
+  VGM_REQUIRE(!A || ddC, "A requested without ddC");
+  cudaStream_t s = (cudaStream_t)stream;
+  CholWs w;
+  VGM_TRY(chol_ws_carve(ws, ws_bytes, T, ld, w));
+  const size_t mat = (size_t)T * ld, mat_al = align_up(mat * sizeof(double), 256) / sizeof(double);
+  double *LUm = w.extra, *UT = w.extra + mat_al, *V = w.extra + 2 * mat_al;
+  VGM_CUDA_OK(cudaMemcpyAsync(LUm, C, mat * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  VGM_CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(int), s));
+  lu_single_cta_kernel<<<1, 1024, 0, s>>>(LUm, ld, T, w.perm, w.flag);
+  VGM_LAUNCH_OK();
+  lu_unpack_kernel<<<dim3(ceil_div(ld, 128), T), 128, 0, s>>>(LUm, ld, T, w.L, UT);
+  VGM_LAUNCH_OK();
+  VGM_TRY(transpose(w.L, ld, w.LT, ld, T, T, s));
+  // P C = Lu U  =>  D = dC C^-1 = (dC U^-1 Lu^-1) P                  GP_regression.py:306
+  VGM_CUDA_OK(cudaMemcpyAsync(V, dC, mat * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  VGM_TRY(tri_solve_right(UT, w.L, w.LT, ld, T, V, ld, T, s));
+  VGM_CUDA_OK(cudaMemsetAsync(D, 0, mat * sizeof(double), s));
+  permute_cols_kernel<<<dim3(ceil_div(T, 128), T), 128, 0, s>>>(V, ld, D, ld, T, w.perm);
+  VGM_LAUNCH_OK();
+  if (A) {
+    vgm_gemm_args g;                                                 // A = ddC - D dC^T, :317
+    memset(&g, 0, sizeof(g));
+    g.A = D; g.lda = ld;
+    g.B = dC; g.ldb = ld;
+    g.C = A; g.ldc = ld; g.C0 = ddC;
+    g.N = T; g.M = T; g.K = T;
+    g.alpha = -1.0; g.beta = 1.0;
+    VGM_TRY(dgemm_nt(g, s));
+  }
+  int flag = 0;
+  VGM_CUDA_OK(cudaMemcpyAsync(&flag, w.flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  VGM_CUDA_OK(cudaStreamSynchronize(s));
+  if (flag != 0) {
+    set_error("LU: column %d has no non-zero pivot (matrix singular)", flag - 1);
+    return VGM_ENOTSPD;
   }
   return VGM_OK;
 }
