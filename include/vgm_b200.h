@@ -224,6 +224,9 @@ typedef struct {
                            (vgm_band_halfwidth); <= 0: dense                                                  */
   int band_M_lp, band_G; /* half band widths used on the low-precision side: M at ~2^-20 (the bf16-split product
                            resolves 2^-16), G at ~2^-7 (a preconditioner only has to stay SPD); <= 0: dense   */
+  const double* DtD;    /* optional D^T D, [T][ld]: with T <= 160 it enables the direct per-CTA solver for systems
+                           whose R_uu varies in time (each CTA forms D^T D - diag(R) D - D^T diag(R) +
+                           diag(R^2 + Lambda) in shared memory and factorises it); constant R_uu uses M          */
 } vgm_operators;
 int vgm_convert_bf16(const double* in, void* out_bf16, int rows, int ld, vgm_stream_t stream);
 int vgm_split_bf16(const double* in, void* out_bf16x2, int rows, int ld, vgm_stream_t stream);
@@ -246,6 +249,9 @@ typedef struct {
   int small_level_solver; /* 1: dependency levels of <= 8 systems are solved by one CTA per system (FP32 banded Cholesky
                             + FP64 refinement in a single launch, csrc/small_solve.cu) instead of the batched solver.
                             Off by default: at T=1000 it takes 1.4 ms against 1.1 ms for the ~190 tiny launches  */
+  int dense_short_grids;  /* 0 (default): systems with T <= 160 are formed and factorised directly, one CTA per system
+                             (FP64 Cholesky in shared memory), falling back to the iterative solvers on a non-positive
+                             pivot; -1: never */
 } vgm_solver_opts;
 
 typedef struct {

@@ -59,12 +59,13 @@ class SweepPlan(C.Structure):
 class Operators(C.Structure):
     _fields_ = [("D", c_dp), ("DT", c_dp), ("M", c_dp), ("G", c_dp), ("G_bf16", c_dp), ("M_bf16x2", c_dp),
                 ("G_shift", C.c_double), ("precond_c", C.c_double),
-                ("band_D", C.c_int), ("band_M", C.c_int), ("band_M_lp", C.c_int), ("band_G", C.c_int)]
+                ("band_D", C.c_int), ("band_M", C.c_int), ("band_M_lp", C.c_int), ("band_G", C.c_int),
+                ("DtD", c_dp)]
 
 
 class SolverOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("check_every", C.c_int), ("inner_iters", C.c_int),
-                ("optimistic_passes", C.c_int), ("small_level_solver", C.c_int)]
+                ("optimistic_passes", C.c_int), ("small_level_solver", C.c_int), ("dense_short_grids", C.c_int)]
 
 
 class SweepInfo(C.Structure):

@@ -25,6 +25,7 @@
 #include "tc_gemm.cuh"
 #include "refine.cuh"
 #include "small_solve.cuh"
+#include "dense_solve.cuh"
 
 struct vgm_program;
 
@@ -696,6 +697,27 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
   VGM_REQUIRE(ops && ops->D && ops->DT, "operators D and DT are required");
   VGM_REQUIRE(!ruu_const || ops->M, "shared operator M is required when R_uu is constant");
   VGM_REQUIRE(ruu_const || Ruu, "R_uu array is required when it is not constant");
+  // short time grids: one CTA per system forms its matrix in shared memory and solves it directly
+  if (!(opts && opts->dense_short_grids < 0) && dense_solve_applicable(ops, ruu_const, T)) {
+    DenseSolveArgs da;
+    memset(&da, 0, sizeof(da));
+    da.M = ruu_const ? ops->M : nullptr;
+    da.D = ops->D; da.DT = ops->DT; da.DtD = ops->DtD; da.T = T; da.ld = ld;
+    da.Ruu = Ruu; da.Lambda = Lambda; da.rhs = rhs; da.X = X;
+    da.slot_state = slot_state; da.slot_has_self = slot_has_self; da.rows = rows;
+    da.bad = w.cb.n_act + 32;
+    VGM_CUDA_OK(cudaMemsetAsync(da.bad, 0, sizeof(int), s));
+    VGM_TRY(dense_solve(da, n_rows, s));
+    int bad = 0;
+    VGM_CUDA_OK(cudaMemcpyAsync(&bad, da.bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGM_CUDA_OK(cudaStreamSynchronize(s));
+    cnt.launches += 1;
+    if (bad == 0) {
+      if (info) info->iterations = max(info->iterations, 1);
+      return VGM_OK;
+    }
+    if (g_debug) fprintf(stderr, "[vgm] dense solver: non-positive pivot in slot %d, iterative solver takes over\n", bad - 1);
+  }
   // a handful of systems (the wrap-around state, a level of an all-hidden chain): one CTA per system does the
   // whole banded-Cholesky + refinement solve in a single launch
   if (opts && opts->small_level_solver && ops->M_bf16x2 && small_solve_applicable(ops, ruu_const, n_rows, T)) {

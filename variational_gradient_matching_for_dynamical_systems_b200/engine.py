@@ -55,6 +55,7 @@ class Operators:
         self.G_shift = None
         self.band_M = self.band_M_lp = self.band_G = 0
         self.band_D = self.band_of(self.D)
+        self.DtD = None
 
     # |B[i][j]| <= 2^-64 max|B| beyond the band: dropping it perturbs any product by less than half an
     # ulp of its normwise rounding error, so the banded GEMMs stay FP64-exact in the backward sense.
@@ -73,6 +74,21 @@ class Operators:
         out = torch.zeros((self.T, self.ld), dtype=torch.float64, device=self.dev)
         out[:, :self.T] = torch.as_tensor(M, dtype=torch.float64, device=self.dev)[:, :self.T]
         return out
+
+    DENSE_MAX_T = 160       # csrc/dense_solve.cuh
+
+    def ensure_DtD(self):
+        """D^T D for the direct per-CTA solver of systems with time-varying R_uu (T <= DENSE_MAX_T)."""
+        if self.DtD is None:
+            lib = _lib.load()
+            self.DtD = torch.zeros_like(self.D)
+            g = _lib.GemmArgs()
+            g.A, g.B, g.C = self.DT.data_ptr(), self.DT.data_ptr(), self.DtD.data_ptr()
+            g.lda = g.ldb = g.ldc = self.ld
+            g.N, g.M, g.K = self.T, self.T, self.T
+            g.alpha = 1.0
+            _lib.check(lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
+        return self.DtD
 
     def ensure_shared_M(self, c):
         """M = (c I - D)^T (c I - D): the shared system matrix when R_uu == c for every state
@@ -292,8 +308,9 @@ class VGMEngine:
         if solver == "mixed" and not can_mix:
             raise ValueError("solver='mixed' needs constant R_uu, precondition=True and T >= %d" % self.MIXED_MIN_T)
         self.solver = "mixed" if (solver in ("auto", "mixed") and can_mix) else "pcg"
+        # solver='auto' lets short time grids (T <= 160) take the direct per-CTA solver; an explicit choice is honoured
         self.opts = _lib.SolverOpts(tol, max_iter, check_every, int(inner_iters), int(optimistic_passes),
-                                    1 if small_level_solver else 0)
+                                    1 if small_level_solver else 0, 0 if solver == "auto" else -1)
         self.X = torch.zeros((self.K, self.ld), dtype=torch.float64, device=self.dev)
         self.DX = torch.zeros_like(self.X)
         self.theta = torch.zeros(max(self.p, 1), dtype=torch.float64, device=self.dev)
@@ -302,6 +319,8 @@ class VGMEngine:
         self._cops = _lib.Operators()
         self._cops.D, self._cops.DT = self.ops.D.data_ptr(), self.ops.DT.data_ptr()
         self._cops.band_D = self.ops.band_D
+        if not self.plan.c.ruu_const and self.T <= Operators.DENSE_MAX_T:
+            self._cops.DtD = self.ops.ensure_DtD().data_ptr()
         if self.plan.c.ruu_const:
             self._cops.M = self.ops.ensure_shared_M(self.plan.c.ruu_value).data_ptr()
             self._cops.band_M = self.ops.band_M
