@@ -124,6 +124,34 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_kernel(const DenseSol
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int blk_off(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
 
+// Cholesky of one 8 x 8 diagonal block by one warp: lane r (< 8) owns row r, pivot rows travel by shuffle, rsqrt
+// replaces sqrt + divide; the strict upper triangle is zeroed and 1 / L[c][c] goes to dinv.
+__device__ __forceinline__ void factor_diag_block(double* Lpp, double* dinv, int lane, int* s_bad) {
+  const int r = lane & 7;
+  double w[8];
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const double2 t2 = *reinterpret_cast<const double2*>(Lpp + r * 8 + k);
+    w[k] = t2.x;
+    w[k + 1] = t2.y;
+  }
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    double v = w[cc];
+#pragma unroll
+    for (int k = 0; k < cc; ++k) v -= w[k] * __shfl_sync(0xffffffffu, w[k], cc);
+    const double dd = __shfl_sync(0xffffffffu, v, cc);
+    if (!(dd > 0.0) && lane == 0) *s_bad = 1;
+    const double si = rsqrt(dd);
+    w[cc] = (r == cc) ? dd * si : (r > cc ? v * si : 0.0);
+    if (lane == cc) dinv[cc] = si;
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(Lpp + r * 8 + k) = make_double2(w[k], w[k + 1]);
+  }
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const DenseSolveArgs a) {
   extern __shared__ double sm[];
@@ -151,55 +179,42 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const 
     y[t] = t < T ? a.rhs[so + t] : 0.0;
   }
   __syncthreads();
-  // block rows up to and including the diagonal block; padding rows/columns are the identity
-  for (int i = warp; i < Tp; i += NW) {
-    const int I = i >> 3, jend = 8 * (I + 1);
-    double* wrow = Wb + blk_off(I, 0) + (i & 7) * 8;
-    const double ri = Rv[i];
-    const double *m = a.M ? a.M + (size_t)i * ld : nullptr, *p = a.DtD + (size_t)i * ld, *d = a.D + (size_t)i * ld,
-                 *dt = a.DT + (size_t)i * ld;
-    for (int j = lane; j < jend; j += 32) {
-      double v = (i == j) ? 1.0 : 0.0;
-      if (i < T && j <= i) {
-        v = m ? m[j] : p[j] - ri * d[j] - Rv[j] * dt[j];
-        if (j == i) v += ri * ri + a.Lambda[so + i];
+  // the lower block triangle, one 8 x 8 block per warp pass (two entries per lane, six independent L2 reads in
+  // flight); padding rows/columns are the identity
+  {
+    const int n_blk = nb * (nb + 1) / 2;
+    int I = 0, J = 0;                             // block coordinates of flat index b (advanced incrementally)
+    for (int b = 0; b < warp; ++b) { if (++J > I) { ++I; J = 0; } }
+    for (int b = warp; b < n_blk; b += NW) {
+      double* blk = Wb + b * 64;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int e = lane + 32 * h, r = e >> 3, cc = e & 7, i = 8 * I + r, j = 8 * J + cc;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < T && j <= i) {
+          if (a.M) {
+            v = a.M[(size_t)i * ld + j];
+          } else {
+            const size_t o = (size_t)i * ld + j;
+            v = a.DtD[o] - Rv[i] * a.D[o] - Rv[j] * a.DT[o];
+            if (j == i) v += Rv[i] * Rv[i];
+          }
+          if (j == i) v += a.Lambda[so + i];
+        }
+        blk[e] = v;
       }
-      wrow[(j >> 3) * 64 + (j & 7)] = v;
+      for (int st = 0; st < NW; ++st) { if (++J > I) { ++I; J = 0; } }
     }
   }
   __syncthreads();
 
   const int g = lane >> 2, q = lane & 3;          // DMMA fragment coordinates
+  if (warp == 0) factor_diag_block(Wb, dinv, lane, &s_bad);
+  __syncthreads();
   for (int pnl = 0; pnl < nb; ++pnl) {
     const int c0 = 8 * pnl;
     double* Lpp = Wb + blk_off(pnl, pnl);
-    // ---- 1. diagonal block, warp 0: lane r (< 8) owns row r ----
-    if (warp == 0) {
-      const int r = lane & 7;
-      double w[8];
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        const double2 t2 = *reinterpret_cast<const double2*>(Lpp + r * 8 + k);
-        w[k] = t2.x;
-        w[k + 1] = t2.y;
-      }
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        double v = w[cc];
-#pragma unroll
-        for (int k = 0; k < cc; ++k) v -= w[k] * __shfl_sync(0xffffffffu, w[k], cc);
-        const double dd = __shfl_sync(0xffffffffu, v, cc);
-        if (!(dd > 0.0) && lane == 0) s_bad = 1;
-        const double si = rsqrt(dd);
-        w[cc] = (r == cc) ? dd * si : (r > cc ? v * si : 0.0);
-        if (lane == cc) dinv[c0 + cc] = si;
-      }
-      if (lane < 8) {
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(Lpp + r * 8 + k) = make_double2(w[k], w[k + 1]);
-      }
-    }
-    __syncthreads();
+    // ---- 1. the diagonal block was factorised by warp 0 at the end of the previous panel's step 3 ----
     // ---- 2. panel: rows below the diagonal block, plus the right-hand side as one more row ----
     {
       const int n_below = Tp - c0 - 8;
@@ -226,20 +241,40 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const 
       }
     }
     __syncthreads();
-    // ---- 3. trailing update on the tensor cores, blocks dealt round-robin to the warps ----
+    // ---- 3. trailing update on the tensor cores.  Warp 0 updates the next diagonal block and factorises it right
+    //         away (step 1 of the next panel, off the critical path); the other warps share the remaining blocks ----
     {
-      int idx = 0;
-      for (int I = pnl + 1; I < nb; ++I) {
-        const double2 af = *reinterpret_cast<const double2*>(Wb + blk_off(I, pnl) + g * 8 + 2 * q);
-        for (int J = pnl + 1; J <= I; ++J, ++idx) {
-          if (idx % NW != warp) continue;
-          const double2 bf = *reinterpret_cast<const double2*>(Wb + blk_off(J, pnl) + g * 8 + 2 * q);
-          double2* cp = reinterpret_cast<double2*>(Wb + blk_off(I, J) + g * 8 + 2 * q);
+      if (warp == 0) {
+        if (pnl + 1 < nb) {
+          const double2 af = *reinterpret_cast<const double2*>(Wb + blk_off(pnl + 1, pnl) + g * 8 + 2 * q);
+          double2* cp = reinterpret_cast<double2*>(Wb + blk_off(pnl + 1, pnl + 1) + g * 8 + 2 * q);
           const double2 c2 = *cp;
           double cf[2] = {c2.x, c2.y};
-          dmma_8x8x4(cf, -af.x, bf.x);
-          dmma_8x8x4(cf, -af.y, bf.y);
+          dmma_8x8x4(cf, -af.x, af.x);
+          dmma_8x8x4(cf, -af.y, af.y);
           *cp = make_double2(cf[0], cf[1]);
+          __syncwarp();
+          factor_diag_block(Wb + blk_off(pnl + 1, pnl + 1), dinv + c0 + 8, lane, &s_bad);
+        }
+      } else {
+        int base = 0;                             // (blocks dealt so far) mod (NW - 1)
+        for (int I = pnl + 2; I < nb; ++I) {
+          const int n_row = I - pnl;              // blocks (I, pnl+1 .. I)
+          int J = pnl + 1 + ((warp - 1 - base + (NW - 1)) % (NW - 1));
+          if (J <= I) {
+            const double2 af = *reinterpret_cast<const double2*>(Wb + blk_off(I, pnl) + g * 8 + 2 * q);
+            const double nx = -af.x, ny = -af.y;
+            for (; J <= I; J += NW - 1) {
+              const double2 bf = *reinterpret_cast<const double2*>(Wb + blk_off(J, pnl) + g * 8 + 2 * q);
+              double2* cp = reinterpret_cast<double2*>(Wb + blk_off(I, J) + g * 8 + 2 * q);
+              const double2 c2 = *cp;
+              double cf[2] = {c2.x, c2.y};
+              dmma_8x8x4(cf, nx, bf.x);
+              dmma_8x8x4(cf, ny, bf.y);
+              *cp = make_double2(cf[0], cf[1]);
+            }
+          }
+          base = (base + n_row) % (NW - 1);
         }
       }
       // right-hand side: y[j] -= L[j][c0 .. c0+8) . z[c0 .. c0+8)
@@ -254,11 +289,13 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const 
     }
     __syncthreads();
   }
-  // ---- back substitution L^T x = z, panel by panel from the bottom ----
+  // ---- back substitution L^T x = z, panel by panel from the bottom.  The 8 entries of a panel are owned by 8
+  //      neighbouring threads of one warp, so the thread that solves the next diagonal block only needs a warp-level
+  //      sync after that warp's update: one block barrier per panel ----
   for (int pnl = nb - 1; pnl >= 0; --pnl) {
     const int c0 = 8 * pnl;
     const double* Lpp = Wb + blk_off(pnl, pnl);
-    if (tid == 0) {
+    if (tid == c0) {
       double x[8];
 #pragma unroll
       for (int cc = 7; cc >= 0; --cc) {
@@ -277,8 +314,9 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const 
       for (int k = 0; k < 8; ++k) v -= col[k * 8] * xs[c0 + k];
       y[tid] = v;
     }
-    __syncthreads();
+    __syncwarp();
   }
+  __syncthreads();
   if (s_bad) {
     if (tid == 0) atomicCAS(a.bad, 0, slot + 1);
     return;                                       // leave x untouched for the iterative fallback
