@@ -536,6 +536,30 @@ def test_trajectory_batch_pools_the_parameter_statistics(pkg):
     assert relerr(eng.get_states(), Xref) < TOL, eng.last_info
 
 
+@pytest.mark.parametrize("fname,lines_from_golden", [("lorenz96_K8_T30_allhidden.npz", False),
+                                                     ("lotka_volterra_T50.npz", True),
+                                                     ("protein_transduction_T99.npz", True),
+                                                     ("lorenz_attractor_T150.npz", True)])
+def test_dense_short_grid_solver_matches_fp64_pcg(pkg, fname, lines_from_golden):
+    """T <= 160: solver='auto' forms each system in shared memory and factorises it (csrc/dense_solve.cu; 64, 128 and
+    192-thread variants, shared M and time-varying R_uu); solver='pcg' is the iterative FP64 path.  Both must agree
+    with each other far below the parity tolerance and with the reference golden."""
+    g = load(fname)
+    if lines_from_golden:
+        lines, params, mode = [str(s) for s in g["lines"]], [str(s) for s in g["params"]], "proxy"
+    else:
+        lines, params, mode = vo.lorenz96_ode_lines(len(g["names"])), ["_alpha"], "reference"
+    out = {}
+    for solver in ("auto", "pcg"):
+        eng = _engine_from_golden(pkg, g, lines, params, theta_mode=mode, solver=solver, builtin=False)
+        eng.theta_step()
+        eng.state_sweep()
+        out[solver] = (eng.get_states(), eng.last_info)
+    assert out["auto"][1]["iterations"] == 1 and out["pcg"][1]["iterations"] > 1, (out["auto"][1], out["pcg"][1])
+    assert relerr(out["auto"][0], out["pcg"][0]) < 1e-11
+    assert relerr(out["auto"][0], g["states"][0]) < TOL
+
+
 def test_lorenz96_K1000_T1000_vs_oracle(pkg):
     """Config C3 (Lorenz96 K=1000, T=1000): full iteration against the NumPy restatement."""
     p, _lib, engine = pkg

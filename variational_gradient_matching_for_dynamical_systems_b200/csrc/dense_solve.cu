@@ -6,112 +6,18 @@
 //       = D^T D - diag(R) D - D^T diag(R) + diag(R^2 + Lambda)          (D^T D is shared: vgm_operators.DtD)
 // (with a constant R_uu = c the shared  M = (c I - D)^T (c I - D)  is read instead)
 //
-// Only the lower triangle is formed (three L2-resident reads per entry) and kept packed, factorised left-looking in
-// shared memory, the right-hand side rides along as row T (forward substitution for free), and a
-// right-looking back substitution finishes.  FP64 throughout; a non-positive pivot is reported and the caller falls back to the iterative solver.
+// Only the lower block triangle is formed (three L2-resident reads per entry), the right-hand side rides along as
+// one more row (forward substitution for free) and a blocked back substitution finishes.  FP64 throughout, the same
+// backward-stable direct solve the reference's LAPACK call performs; a non-positive pivot is reported and the
+// caller falls back to the iterative solver.
 #include "dense_solve.cuh"
 #include "vgm_common.cuh"
 #include "vgm_profile.cuh"
 
 namespace vgm {
 
-// Factorisation: M = W Dg^-1 W^T with W lower triangular and Dg = diag(W) (Cholesky without the square roots, so a
-// column needs nothing from the pivot thread before it is complete and ONE barrier per column suffices):
-//   W[i][c] = M[i][c] - sum_{k<c} W[i][k] W[c][k] / W[k][k]                        i >= c
-// Thread i owns row i (row T carries the right-hand side).  The lower triangle is stored packed, rows padded to an
-// even length (16-byte loads): 41 KB at T = 99, so five CTAs share an SM and hide each other's dependent chains.
-// The kernel is shared-memory bound, so the scaled pivot row  S[k] = W[c][k] / W[k][k]  of the NEXT column is
-// prepared by the threads whose rows are already finished (thread k < c scales entry k while column c is being
-// computed): the inner loop is one 16-byte own-row load, one 16-byte broadcast load and two DFMAs per two k.
-__device__ __forceinline__ int tri_row(int i) {      // offset of packed row i (rows padded to even length)
-  const int m = i >> 1;
-  return (i & 1) ? 2 * (m + 1) * (m + 1) : 2 * m * (m + 1);
-}
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) dense_spd_solve_kernel(const DenseSolveArgs a) {
-  extern __shared__ double sm[];
-  const int T = a.T, ld = a.ld, Tp = (T + 2) & ~1;
-  double* W = sm;                                 // packed lower triangle rows 0 .. T, row T = right-hand side
-  double* S = W + tri_row(T + 1);                 // 2 x Tp  scaled pivot rows (double buffered)
-  double* Rv = S + 2 * Tp;                        // Tp    R_uu(t)
-  double* inv = Rv + Tp;                          // Tp    1 / W[k][k]
-  double* xs = inv + Tp;                          // Tp    solution
-  const int tid = threadIdx.x;
-  const int slot = a.rows[blockIdx.x];
-  const size_t so = (size_t)slot * ld;
-  double* xout = a.X + (size_t)a.slot_state[slot] * ld;
-  const bool has_self = a.slot_has_self ? a.slot_has_self[slot] != 0 : true;
-  if (!has_self) {
-    // u not in c(u): the reference's aliasing doubles the diagonal and there is no B_uu term
-    for (int t = tid; t < T; t += THREADS) xout[t] = a.rhs[so + t] / (2.0 * a.Lambda[so + t]);
-    return;
-  }
-  const int rowT = tri_row(T);
-  for (int t = tid; t < T; t += THREADS) {
-    Rv[t] = a.M ? 0.0 : a.Ruu[so + t];
-    W[rowT + t] = a.rhs[so + t];
-  }
-  __syncthreads();
-  // lower triangle, row by row: warp lanes run along j (coalesced reads of the L2-resident operators)
-  for (int i = tid >> 5; i < T; i += THREADS >> 5) {
-    double* wi = W + tri_row(i);
-    if (a.M) {
-      const double* m = a.M + (size_t)i * ld;
-      for (int j = tid & 31; j <= i; j += 32) wi[j] = m[j] + (j == i ? a.Lambda[so + i] : 0.0);
-    } else {
-      const double ri = Rv[i];
-      const double *p = a.DtD + (size_t)i * ld, *d = a.D + (size_t)i * ld, *dt = a.DT + (size_t)i * ld;
-      for (int j = tid & 31; j <= i; j += 32) {
-        double v = p[j] - ri * d[j] - Rv[j] * dt[j];
-        if (j == i) v += ri * ri + a.Lambda[so + i];
-        wi[j] = v;
-      }
-    }
-  }
-  __syncthreads();
-  const int i = tid;
-  double* Wi = W + tri_row(min(i, T));
-  for (int c = 0; c < T; ++c) {
-    const double* Sc = S + (c & 1) * Tp;          // S[k] = W[c][k] inv[k] for k < c - 1 (made during column c - 1)
-    if (i >= c && i <= T) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      const int n = c - 1;                        // entries served by Sc
-      int k = 0;
-      for (; k + 4 <= n; k += 4) {
-        const double2 w0 = *reinterpret_cast<const double2*>(Wi + k), s0 = *reinterpret_cast<const double2*>(Sc + k);
-        const double2 w1 = *reinterpret_cast<const double2*>(Wi + k + 2), s1 = *reinterpret_cast<const double2*>(Sc + k + 2);
-        a0 += w0.x * s0.x;
-        a1 += w0.y * s0.y;
-        a2 += w1.x * s1.x;
-        a3 += w1.y * s1.y;
-      }
-      for (; k < n; ++k) a0 += Wi[k] * Sc[k];
-      if (c >= 1) a1 += Wi[c - 1] * (W[tri_row(c) + c - 1] * inv[c - 1]);   // column c - 1 was finished last
-      const double v = Wi[c] - ((a0 + a1) + (a2 + a3));
-      Wi[c] = v;
-      if (i == c) {
-        if (!(v > 0.0)) atomicCAS(a.bad, 0, slot + 1);
-        inv[c] = 1.0 / v;
-      }
-    } else if (i < c) {
-      // finished rows: scale entry i of the next pivot row (row c + 1 <= T always exists; row T is the rhs)
-      S[((c + 1) & 1) * Tp + i] = W[tri_row(c + 1) + i] * inv[i];
-    }
-    __syncthreads();
-  }
-  // W Dg^-1 W^T x = b: row T now holds u = (W Dg^-1)^-1 b; back substitution x_j = (u_j - sum_{k>j} W[k][j] x_k) / W[j][j]
-  double t = (i < T) ? W[rowT + i] : 0.0;
-  for (int c = T - 1; c >= 0; --c) {
-    if (i == c) xs[c] = t * inv[c];
-    __syncthreads();
-    if (i < c) t -= W[tri_row(c) + i] * xs[c];
-  }
-  if (i < T) xout[i] = xs[i];
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// Blocked variant (the default): right-looking Cholesky on 8 x 8 blocks.  The lower block triangle lives in shared
+// Right-looking Cholesky on 8 x 8 blocks.  The lower block triangle lives in shared
 // memory block by block (64 contiguous doubles each: 46 KB at T = 99, four CTAs per SM); per panel
 //   1. warp 0 factorises the diagonal block in registers (lane = row, pivot rows travel by shuffle, rsqrt instead
 //      of sqrt + divide),
@@ -119,8 +25,9 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_kernel(const DenseSol
 //      forward substitution rides along),
 //   3. the trailing blocks get  C -= A B^T  on the FP64 tensor cores: one m8n8k4 DMMA pair per 8 x 8 block, the
 //      fragments are single 16-byte loads because a block is stored exactly in fragment order.
-// Three barriers per panel instead of one per column, ~4x fewer instructions and ~7x fewer shared-memory
-// wavefronts than the column version below.
+// Two barriers per panel (the next diagonal block is factorised by warp 0 inside step 3).  A first version with one
+// thread per row and one barrier per column (left-looking, packed triangle) needed 3x the instructions and 2.6x the
+// shared-memory wavefronts: 26 ms against 10.5 ms for the 131 072 systems of config C4.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int blk_off(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
 
@@ -187,21 +94,35 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const 
     for (int b = 0; b < warp; ++b) { if (++J > I) { ++I; J = 0; } }
     for (int b = warp; b < n_blk; b += NW) {
       double* blk = Wb + b * 64;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int e = lane + 32 * h, r = e >> 3, cc = e & 7, i = 8 * I + r, j = 8 * J + cc;
-        double v = (i == j) ? 1.0 : 0.0;
-        if (i < T && j <= i) {
+      if (J < I) {
+        // off-diagonal block: every entry is below the diagonal; lane = (row lane / 4, column pair lane % 4)
+        const int r = lane >> 2, cc = 2 * (lane & 3), i = 8 * I + r, j = 8 * J + cc;
+        double2 v = make_double2(0.0, 0.0);
+        if (i < T) {
+          const size_t o = (size_t)i * ld + j;
           if (a.M) {
-            v = a.M[(size_t)i * ld + j];
+            v = *reinterpret_cast<const double2*>(a.M + o);
           } else {
-            const size_t o = (size_t)i * ld + j;
-            v = a.DtD[o] - Rv[i] * a.D[o] - Rv[j] * a.DT[o];
-            if (j == i) v += Rv[i] * Rv[i];
+            const double2 pv = *reinterpret_cast<const double2*>(a.DtD + o), dv = *reinterpret_cast<const double2*>(a.D + o),
+                          tv = *reinterpret_cast<const double2*>(a.DT + o);
+            const double ri = Rv[i];
+            v.x = pv.x - ri * dv.x - Rv[j] * tv.x;
+            v.y = pv.y - ri * dv.y - Rv[j + 1] * tv.y;
           }
-          if (j == i) v += a.Lambda[so + i];
         }
-        blk[e] = v;
+        *reinterpret_cast<double2*>(blk + r * 8 + cc) = v;
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = lane + 32 * h, r = e >> 3, cc = e & 7, i = 8 * I + r, j = 8 * J + cc;
+          double v = (i == j) ? 1.0 : 0.0;
+          if (i < T && j <= i) {
+            const size_t o = (size_t)i * ld + j;
+            v = a.M ? a.M[o] : a.DtD[o] - Rv[i] * a.D[o] - Rv[j] * a.DT[o];
+            if (j == i) v += (a.M ? 0.0 : Rv[i] * Rv[i]) + a.Lambda[so + i];
+          }
+          blk[e] = v;
+        }
       }
       for (int st = 0; st < NW; ++st) { if (++J > I) { ++I; J = 0; } }
     }
@@ -229,12 +150,12 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const 
           x[k] = t2.x;
           x[k + 1] = t2.y;
         }
+        // column-oriented so that only one multiply and one FMA per step sit on the dependent chain
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
-          double v = x[cc];
+          x[cc] *= dinv[c0 + cc];
 #pragma unroll
-          for (int k = 0; k < cc; ++k) v -= x[k] * Lpp[cc * 8 + k];
-          x[cc] = v * dinv[c0 + cc];
+          for (int k = cc + 1; k < 8; ++k) x[k] -= x[cc] * Lpp[k * 8 + cc];
         }
 #pragma unroll
         for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(xp + k) = make_double2(x[k], x[k + 1]);
@@ -298,11 +219,12 @@ __global__ void __launch_bounds__(THREADS) dense_spd_solve_blocked_kernel(const 
     if (tid == c0) {
       double x[8];
 #pragma unroll
-      for (int cc = 7; cc >= 0; --cc) {
-        double v = y[c0 + cc];
+      for (int k = 0; k < 8; ++k) x[k] = y[c0 + k];
 #pragma unroll
-        for (int k = cc + 1; k < 8; ++k) v -= Lpp[k * 8 + cc] * x[k];
-        x[cc] = v * dinv[c0 + cc];
+      for (int cc = 7; cc >= 0; --cc) {
+        x[cc] *= dinv[c0 + cc];
+#pragma unroll
+        for (int k = 0; k < cc; ++k) x[k] -= Lpp[cc * 8 + k] * x[cc];
         xs[c0 + cc] = x[cc];
       }
     }
@@ -329,20 +251,12 @@ static size_t dense_blocked_smem_bytes(int T) {
   return ((size_t)(nb * (nb + 1) / 2) * 64 + 4 * (size_t)nb * 8) * sizeof(double);
 }
 
-static size_t dense_smem_bytes(int T) {
-  const int n = T + 1, m = n >> 1;                                     // tri_row(T + 1) on the host
-  const size_t tri = (n & 1) ? 2 * (size_t)(m + 1) * (m + 1) : 2 * (size_t)m * (m + 1);
-  return (tri + 5 * (size_t)((T + 2) & ~1)) * sizeof(double);
-}
-
 static const bool g_no_dense = getenv("VGM_NO_DENSE") != nullptr;
 
 bool dense_solve_applicable(const vgm_operators* ops, int ruu_const, int T) {
   if (g_no_dense || !ops || T < 2 || T > DENSE_MAX_T) return false;
   return ruu_const ? ops->M != nullptr : (ops->DtD && ops->D && ops->DT);
 }
-
-static const bool g_dense_columns = getenv("VGM_DENSE_COLUMNS") != nullptr;   // A/B switch: the column version
 
 template <int THREADS>
 static int launch_blocked(const DenseSolveArgs& a, int n_sys, cudaStream_t s) {
@@ -359,34 +273,13 @@ static int launch_blocked(const DenseSolveArgs& a, int n_sys, cudaStream_t s) {
   return VGM_OK;
 }
 
-template <int THREADS>
-static int launch(const DenseSolveArgs& a, int n_sys, cudaStream_t s) {
-  const size_t smem = dense_smem_bytes(a.T);
-  static size_t configured = 0;
-  if (smem > configured) {
-    VGM_CUDA_OK(cudaFuncSetAttribute(dense_spd_solve_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VGM_CUDA_OK(cudaFuncSetAttribute(dense_spd_solve_kernel<THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    configured = smem;
-  }
-  // forms T^2/2 entries from three operators (L2) and reads/writes 4 vectors; T^3/3 + 2 T^2 flops per system
-  ProfScope prof(PROF_VEC, (double)n_sys * ((double)a.T * a.T * a.T / 3.0 + 4.0 * a.T * a.T), (double)n_sys * a.T * 40.0, s);
-  dense_spd_solve_kernel<THREADS><<<n_sys, THREADS, smem, s>>>(a);
-  VGM_LAUNCH_OK();
-  return VGM_OK;
-}
-
 int dense_solve(const DenseSolveArgs& a, int n_sys, cudaStream_t s) {
   if (n_sys <= 0) return VGM_OK;
   VGM_REQUIRE(a.T <= DENSE_MAX_T, "dense solver: T too large");
-  if (!g_dense_columns) {
-    const int rows = (a.T + 7) / 8 * 8 - 8 + 1;          // panel rows of the first panel + the right-hand side
-    if (rows <= 64) return launch_blocked<64>(a, n_sys, s);
-    if (rows <= 128) return launch_blocked<128>(a, n_sys, s);
-    return launch_blocked<192>(a, n_sys, s);
-  }
-  if (a.T + 1 <= 64) return launch<64>(a, n_sys, s);
-  if (a.T + 1 <= 128) return launch<128>(a, n_sys, s);
-  return launch<192>(a, n_sys, s);
+  const int rows = (a.T + 7) / 8 * 8 - 8 + 1;            // panel rows of the first panel + the right-hand side
+  if (rows <= 64) return launch_blocked<64>(a, n_sys, s);
+  if (rows <= 128) return launch_blocked<128>(a, n_sys, s);
+  return launch_blocked<192>(a, n_sys, s);
 }
 
 }  // namespace vgm
