@@ -173,6 +173,8 @@ class HaloExchange:
                 owner = int(np.searchsorted(bounds, s, side="right") - 1)
                 send[owner].append(int(s))
         send = [sorted(set(v)) for v in send]
+        # trajectory batches: nobody reads anybody's rows, so there is no exchange at all (same answer on every rank)
+        self.empty = all(len(v) == 0 for v in send)
         self.n_pub = max(1, max(len(v) for v in send))
         self.pub_rows_local = np.array([s - loc.k0 for s in send[self.rank]], dtype=np.int64)
         pos = [{s: i for i, s in enumerate(v)} for v in send]
@@ -184,7 +186,7 @@ class HaloExchange:
 
     def __call__(self, X):
         """X: [n_rows, ld] tensor of this rank (owned rows first); halo rows are overwritten."""
-        if self.world == 1 and len(self.src_flat) == 0:
+        if self.empty:
             return
         ld = X.shape[1]
         if self._buf is None or self._buf[0].shape[1] != ld or self._buf[0].device != X.device:
