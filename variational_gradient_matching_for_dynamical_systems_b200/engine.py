@@ -264,7 +264,8 @@ class VGMEngine:
         hard-coded at proxies...py:211) into R_uk, r_uk; 'proxy' plugs the current estimate.
     solver : 'mixed' = FP64 residuals on the DMMA pipe + FP32 PCG corrections whose operator products run
         on the tcgen05 tensor cores (bf16-split operands); 'pcg' = FP64 preconditioned CG only;
-        'auto' = 'mixed' whenever the model allows it (R_uu constant, T >= MIXED_MIN_T).
+        'auto' = the direct per-CTA solver ('dense', csrc/dense_solve.cu) for T <= 160, else 'mixed' whenever the
+        model allows it (R_uu constant, T >= MIXED_MIN_T), else 'pcg'.  ``self.solver`` holds the resolved choice.
     """
     MIXED_MIN_T = 128
     # preconditioner S G S of the mixed-precision solver: G = (M + SHIFT_FRAC mean(Lambda) I)^-1,
@@ -307,7 +308,9 @@ class VGMEngine:
         can_mix = bool(self.plan.c.ruu_const) and self.precondition and self.T >= self.MIXED_MIN_T
         if solver == "mixed" and not can_mix:
             raise ValueError("solver='mixed' needs constant R_uu, precondition=True and T >= %d" % self.MIXED_MIN_T)
-        self.solver = "mixed" if (solver in ("auto", "mixed") and can_mix) else "pcg"
+        # 'dense' (only through solver='auto'): T <= 160, every system is formed and factorised by its own CTA
+        can_dense = solver == "auto" and self.T <= Operators.DENSE_MAX_T
+        self.solver = "dense" if can_dense else ("mixed" if (solver in ("auto", "mixed") and can_mix) else "pcg")
         # solver='auto' lets short time grids (T <= 160) take the direct per-CTA solver; an explicit choice is honoured
         self.opts = _lib.SolverOpts(tol, max_iter, check_every, int(inner_iters), int(optimistic_passes),
                                     1 if small_level_solver else 0, 0 if solver == "auto" else -1)
@@ -363,7 +366,7 @@ class VGMEngine:
 
     # ---- preconditioner -----------------------------------------------------------------------
     def _prepare_preconditioner(self):
-        if not (self.precondition and self.plan.c.ruu_const) or self.plan.n_hidden == 0:
+        if not (self.precondition and self.plan.c.ruu_const) or self.plan.n_hidden == 0 or self.solver == "dense":
             self._cops.G = None
             self._cops.G_bf16 = None
             self._cops.M_bf16x2 = None
