@@ -560,6 +560,46 @@ def test_dense_short_grid_solver_matches_fp64_pcg(pkg, fname, lines_from_golden)
     assert relerr(out["auto"][0], g["states"][0]) < TOL
 
 
+def test_lorenz_attractor_T1000_vs_oracle(pkg):
+    """Config C2 (BASELINE.json configs[1]): Lorenz attractor, 3 states / 3 parameters, T = 1000 grid points
+    (dt = 0.02), _x and _z observed at every grid point, _y hidden; rbf kernel with l = 1.25 dt.
+    Two full iterations against the oracle restatement (patched semantics: the current theta enters R, r)."""
+    import sympy as sym
+    p, _lib, engine = pkg
+    g = load("lorenz_attractor_T150.npz")
+    lines, params, names = [str(s) for s in g["lines"]], [str(s) for s in g["params"]], [str(s) for s in g["names"]]
+    T, dt = 1000, 0.02
+
+    def f(v):
+        x, y, z = v
+        return np.array([10.0 * (y - x), 28.0 * x - y - x * z, x * y - 8.0 / 3.0 * z])
+
+    v, h, rows = np.array([1.0, 1.0, 1.0]), 0.01, []
+    for n in range(2 * T):                                        # RK4, two steps per grid point
+        if n % 2 == 0:
+            rows.append(v.copy())
+        k1 = f(v); k2 = f(v + 0.5 * h * k1); k3 = f(v + 0.5 * h * k2); k4 = f(v + h * k3)
+        v = v + h / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+    X0 = np.array(rows)
+    rng = np.random.default_rng(5)
+    X0[:, 1] += 0.5 * rng.standard_normal(T)                     # perturbed initial proxy of the hidden state
+    t = np.arange(T) * dt
+    D, A, *_ = vo.kernel_function(t, t[:2], "rbf", [1.25 * dt, 1.0])
+    sc = [[int(c) for c in str(cs).split(",") if c != ""] for cs in g["couplings"]]
+    lin = vo.Linearisation(vo.parse_ode_lines(lines), sym.symbols(names), sym.symbols(params), couplings=sc)
+    hidden = [1]
+    eng = engine.VGMEngine(p.OdeModel(lines, names, params), D, A, hidden=hidden, couplings=sc, theta_mode="proxy")
+    eng.set_states(X0)
+    X = X0.copy()
+    for it in range(2):
+        th_ref = vo.theta_step(X, lin, D)[0]
+        X, _ = vo.state_sweep(X, th_ref, lin, D, hidden)
+        th = eng.theta_step().cpu().numpy()
+        assert relerr(th, th_ref) < TOL, (it, th, th_ref)
+        eng.state_sweep()
+        assert relerr(eng.get_states(), X) < TOL, (it, eng.last_info)
+
+
 def test_lorenz96_K1000_T1000_vs_oracle(pkg):
     """Config C3 (Lorenz96 K=1000, T=1000): full iteration against the NumPy restatement."""
     p, _lib, engine = pkg
