@@ -290,13 +290,19 @@ def native_arm(args):
         th_h = torch.zeros(max(core.p, 1), dtype=torch.float64, pin_memory=True)
         Xh_out.copy_(X0_local)          # the clamped (observed) rows never change; only updated rows travel back
         h2d = Xh_in.numel() * 8
-        d2h = (core.plan.n_hidden * ld if world == 1 else Xh_out.numel()) * 8 + core.p * 8
+        d2h = core.plan.n_hidden * ld * 8 + core.p * 8
+        if world > 1:
+            # only the rows this rank updated travel back (as at N=1): gathered on the device, one contiguous copy
+            hid_idx = torch.as_tensor(np.asarray(core.plan.hidden, dtype=np.int64), device=dev)
+            stage = torch.empty((len(hid_idx), ld), dtype=torch.float64, device=dev)
+            Xh_hid = torch.empty((len(hid_idx), ld), dtype=torch.float64, pin_memory=True)
 
         def e2e_step():
             if world > 1:
                 core.X.copy_(Xh_in, non_blocking=True)
                 eng.iteration()
-                Xh_out.copy_(core.X, non_blocking=True)
+                torch.index_select(core.X, 0, hid_idx, out=stage)
+                Xh_hid.copy_(stage, non_blocking=True)
                 th_h.copy_(core.theta, non_blocking=True)
                 torch.cuda.synchronize()
             else:
@@ -319,7 +325,7 @@ def native_arm(args):
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
                "api": ("vgm_iteration_host (C ABI, pinned host buffers; %d state ranges pipelined: copy-in, "
                        "solve and copy-out overlap)" % core.last_pipeline) if world == 1 else
-                      "DistributedVGMEngine.iteration with pinned host copies per rank"}
+                      "DistributedVGMEngine.iteration with pinned host copies per rank (all local rows in, updated rows out)"}
 
     if rank != 0:
         if world > 1:
