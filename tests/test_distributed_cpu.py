@@ -129,3 +129,46 @@ def test_halo_exchange_and_allreduce_gloo_world2(tmp_path):
     mp.spawn(_halo_worker, args=(world, port, K, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d.txt" % r)).read() == "ok"
+
+
+PT_LINES = ["-_k_1 * _S - _k_2 * _S * _R + _k_3 * _RS", "_k_1 * _S", "-_k_2 * _S * _R + _k_3 * _RS + _V * _Rpp / (0.3 + _Rpp)",
+            "_k_2 * _S * _R - _k_3 * _RS - _k_4 * _RS", "_k_4 * _RS - _V * _Rpp / (0.3 + _Rpp)"]
+PT_NAMES = ["_S", "_dS", "_R", "_RS", "_Rpp"]
+PT_PARAMS = ["_k_1", "_k_2", "_k_3", "_k_4", "_V"]
+
+
+def _batch_worker(rank, world, port, n_traj, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        K1 = len(PT_NAMES)
+        model = OdeModel(PT_LINES, PT_NAMES, PT_PARAMS, n_copies=n_traj)
+        hidden = [n * K1 + u for n in range(n_traj) for u in (0, 3)]        # _S and _RS of every trajectory
+        hp = build_host_plan(model, hidden)
+        bounds = block_bounds(model.K, world, align=K1)                       # whole trajectories per rank
+        loc = localize(model, hp, bounds[rank], bounds[rank + 1])
+        hx = HaloExchange(loc, bounds)
+        ok = all(b % K1 == 0 for b in bounds) and len(loc.halo_states) == 0 and hx.empty
+        X = torch.full((loc.n_rows, 4), float(rank + 1), dtype=torch.float64)
+        hx(X)                                                                 # no exchange, nothing touched
+        ok = ok and bool((X == float(rank + 1)).all())
+        # every trajectory's ODE rows and hidden slots live on exactly one rank
+        cnt = torch.tensor([loc.n_stats_odes, loc.plan.n_hidden], dtype=torch.int64)
+        dist.all_reduce(cnt)
+        ok = ok and cnt.tolist() == [model.K, len(hidden)]
+        with open(os.path.join(outdir, "rank%d.txt" % rank), "w") as f:
+            f.write("ok" if ok else "bad")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_trajectory_batch_partition_has_no_halo_gloo_world2(tmp_path):
+    """Config C4's sharding: trajectories split across ranks, no cross-trajectory coupling, so the halo
+    exchange is skipped and the only collective left is the all-reduce of the pooled statistics."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_batch_worker, args=(world, port, 6, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d.txt" % r)).read() == "ok"
