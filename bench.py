@@ -61,6 +61,8 @@ def parse():
                          "of the ranges as fractions; a short first range starts the compute early, a short last "
                          "one shortens the final copy-out; 0 = no pipelining")
     ap.add_argument("--no-profile", action="store_true", help="skip the second, per-kernel-instrumented timed region")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of sampled hidden columns + theta")
+    ap.add_argument("--parity-columns", type=int, default=64)
     args = ap.parse_args()
     pc = str(args.pipeline_chunks)
     args.pipeline_chunks = tuple(float(v) for v in pc.split(",")) if "," in pc else int(pc)
@@ -119,6 +121,82 @@ def reference_arm(args):
             "gpu_launches": 0}
     emit(line)
     return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# Parity of the measured configuration against the CPU oracle ("restatement on 64 random
+# hidden columns + theta").  The oracle is the checker only: it never produces anything that is timed or returned.
+# ----------------------------------------------------------------------------------------------
+PARITY_TOL = 1e-9          # BASELINE.json north_star: 1e-9 relative in the ODE-parameter and state posterior means
+
+
+def parity_block(args, eng, core, X0_local, world, rank, K, T, hidden, n_columns):
+    """One step from the initial proxies, then: theta against oracle.lorenz96_theta_step on the full X0 and
+    `n_columns` seeded random hidden columns (always the first hidden state and the wrap-around state K-1, which reads
+    the first one live) against oracle.lorenz96_sweep_columns -- the statements of
+    proxies_for_ode_parameters_and_states.py:58-93,195-262 with the oracle's OWN kernel_function operators.
+    Every rank calls this (the rows are gathered from their owners); rank 0 returns the dict."""
+    import torch
+    import torch.distributed as dist
+    from oracle import vgm_oracle as vo
+    t_par = time.perf_counter()
+    hidden = np.asarray(hidden, dtype=np.int64)
+    rng = np.random.default_rng(20261020)
+    forced = [int(hidden[0]), int(hidden[-1])]
+    pool = np.setdiff1d(hidden, forced)
+    extra = rng.choice(pool, size=max(0, min(n_columns, len(hidden)) - len(forced)), replace=False)
+    cols = sorted(set(forced + extra.tolist()))
+    need_s, need_l = vo.lorenz96_column_needs(cols, K, hidden)
+    core.X.copy_(X0_local)
+    eng.iteration()
+    theta_gpu = float(core.get_theta()[0])
+    res_states = cols + [k for k in need_l if k not in cols]
+    if world > 1:
+        snap_rows = eng.gather_rows(need_s, source=X0_local)[:, :T]
+        res_rows = eng.gather_rows(res_states)[:, :T]
+        keep = core.X.clone()
+        core.X.copy_(X0_local)
+        X0_full = eng.gather_states()                      # [K, T], for the theta check on rank 0
+        core.X.copy_(keep)
+    else:
+        dev = core.X.device
+        snap_rows = X0_local.index_select(0, torch.as_tensor(need_s, device=dev))[:, :T]
+        res_rows = core.X.index_select(0, torch.as_tensor(res_states, device=dev))[:, :T]
+        X0_full = X0_local[:, :T]
+    out = None
+    if rank == 0:
+        snap = {k: snap_rows[i].cpu().numpy() for i, k in enumerate(need_s)}
+        res = {k: res_rows[i].cpu().numpy() for i, k in enumerate(res_states)}
+        tgrid = np.arange(T) * DT
+        D, *_ = vo.kernel_function(tgrid, tgrid[:2], KERNEL["type"], KERNEL["param"])
+        ref = vo.lorenz96_sweep_columns(snap, {k: res[k] for k in need_l}, K, 8.0, D, cols, hidden)
+        rel, absmax, elem = 0.0, 0.0, 0.0
+        worst = None
+        for u in cols:
+            d = np.abs(res[u] - ref[u])
+            r = float(d.max() / max(np.abs(ref[u]).max(), 1e-300))
+            if r > rel:
+                rel, worst = r, u
+            absmax = max(absmax, float(d.max()))
+            # element-wise relative error with an absolute floor of 1e-3 (the states are O(1..10))
+            elem = max(elem, float((d / (np.abs(ref[u]) + 1e-3)).max()))
+        Xh = X0_full.t().contiguous().cpu().numpy()        # [T, K] reference orientation
+        theta_ref = float(vo.lorenz96_theta_step(Xh, D)[0])
+        del Xh
+        rel_theta = abs(theta_gpu - theta_ref) / abs(theta_ref)
+        ok = bool(rel < PARITY_TOL and rel_theta < PARITY_TOL and np.isfinite(rel) and np.isfinite(rel_theta))
+        out = {"config": "C5" if (K == 100000 and T == 1000) else "Lorenz96 K=%d T=%d" % (K, T),
+               "columns": len(cols), "includes_wrap_around_state": True, "live_columns": [int(k) for k in need_l],
+               "max_rel_states": rel, "worst_column": worst, "max_abs_states": absmax,
+               "max_rel_states_elementwise_floor1e-3": elem, "rel_theta": rel_theta, "theta_oracle": theta_ref,
+               "tol": PARITY_TOL, "ok": ok, "n_gpus": world,
+               "oracle": "oracle/vgm_oracle.py: kernel_function + lorenz96_theta_step (full X) + lorenz96_sweep_columns "
+                         "(dense LAPACK solve per column, proxies...py:195-262)",
+               "seconds": round(time.perf_counter() - t_par, 2)}
+    if world > 1:
+        flag = torch.tensor([1 if (out is None or out["ok"]) else 0], device=core.X.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -327,6 +405,11 @@ def native_arm(args):
                        "solve and copy-out overlap)" % core.last_pipeline) if world == 1 else
                       "DistributedVGMEngine.iteration with pinned host copies per rank (all local rows in, updated rows out)"}
 
+    # ---- parity of this very configuration against the oracle (every rank takes part in the gathers) ------
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(args, eng, core, X0_local, world, rank, K, T, hidden, args.parity_columns)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -407,7 +490,8 @@ def native_arm(args):
                        "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
                              (n_hidden_local * core.ld * 8 / 1e6),
                        "profiled_ms_per_step": (ms_prof / args.steps) if ms_prof else None},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": launches,
+            "clocks": clocks,
             "solver_iterations": pcg_iters, "theta": theta, "setup_s": setup_s,
             "evolving_loop": evolving,
             "canonical_flops": {"per_step": F_canon, "tflops": F_canon * args.steps / (ms * 1e-3) / 1e12,
@@ -416,6 +500,9 @@ def native_arm(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY FAILURE against the oracle: %r\n" % (parity,))
+        return 3
     return 0
 
 

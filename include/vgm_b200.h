@@ -207,6 +207,15 @@ typedef struct {
   const int* live_pair_level_ptr_host; /* [n_levels+1] HOST                                  */
   int ruu_const;             /* 1 => R_uu is the same constant for every hidden state        */
   double ruu_value;          /*      that constant (Lorenz96: -1)                            */
+  /* Optional overlap of a tiny tail with the bulk (vgm_state_sweep, vgm_state_sweep_levels).  When every level after
+   * the first holds a handful of systems (Lorenz96 with every second state observed: the wrap-around state alone,
+   * which reads the updated x of the first hidden state live, proxies...py:225) the chain "early level-0 systems ->
+   * level 1 -> ..." is solved on a high-priority side stream, one single-CTA launch per link, while the other
+   * level-0 systems run as one batch.  n_early = 0 (or null pointers) disables it; levels then run one after the
+   * other.  At most 8 early systems, 8 tail systems, 8 levels. */
+  int n_early;               /* level-0 slots whose updated x a later level reads live       */
+  const int* early_slots;    /* [n_early] device                                             */
+  const int* bulk_slots;     /* [level_ptr_host[1] - n_early] device: the other level-0 slots */
 } vgm_sweep_plan;
 
 typedef struct {
@@ -280,6 +289,11 @@ int vgm_state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* plan,
                             vgm_sweep_info* info, vgm_stream_t stream);
 int vgm_state_sweep_level(const vgm_sweep_plan* plan, const vgm_operators* ops, const vgm_solver_opts* opts,
                           double* X, int level, void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
+/* Every level in order after vgm_state_sweep_prepare (what vgm_state_sweep does), including the tail overlap
+ * described in vgm_sweep_plan.  For callers that own all live sources of their systems (a state-block partition
+ * whose cuts no live read crosses) and so need no exchange between levels. */
+int vgm_state_sweep_levels(const vgm_sweep_plan* plan, const vgm_operators* ops, const vgm_solver_opts* opts,
+                           double* X, void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
 
 /* One building block of the sweep, exposed for tests: snapshot coefficients
  * Lambda_u = sum_{k!=u} R_uk^2, rhs_u (without the -B_uu^T r_uu term and without live terms),

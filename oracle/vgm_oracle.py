@@ -368,6 +368,64 @@ def lorenz96_state_sweep(X, alpha_star, D, hidden, return_info=False):
     return X
 
 
+def lorenz96_column_needs(cols, K, hidden):
+    """States whose rows ``lorenz96_sweep_columns`` reads for the hidden columns ``cols``:
+    (snapshot states, live states).  Snapshot: u-3 .. u+3 (the coefficient stencil, SURVEY.md 8a row P4);
+    live: the hidden k in {u-1, u+1, u+2} that precede u in the ascending update order (proxies...py:195),
+    whose D.x_k the reference reads from the already-updated column (:185 alias, :225)."""
+    hid = set(int(h) for h in hidden)
+    snap, live = set(), set()
+    for u in cols:
+        u = int(u)
+        for j in range(-3, 4):
+            snap.add((u + j) % K)
+        for j in (-1, 1, 2):
+            k = (u + j) % K
+            if k in hid and k < u:
+                live.add(k)
+    return sorted(snap), sorted(live)
+
+
+def lorenz96_sweep_columns(snap, live, K, alpha_star, D, cols, hidden):
+    """``lorenz96_state_sweep`` restricted to the hidden columns ``cols`` (the C5 check of SURVEY.md 8d:
+    "restatement on 64 random hidden columns"); same statements as proxies...py:195-262.
+
+    snap : {state index: T-vector} sweep-start snapshot rows (at least ``lorenz96_column_needs(...)[0]``)
+    live : {state index: T-vector} UPDATED rows of the hidden states that precede a requested column in the
+           update order and are read live by it (``lorenz96_column_needs(...)[1]``)
+    Returns {u: x_u}.  Each column costs one dense T x T solve, like the reference."""
+    D = np.asarray(D, dtype=float)
+    T = D.shape[0]
+    W = np.eye(T) + D
+    M = W.T.dot(W)
+    a = float(alpha_star)
+    hid = set(int(h) for h in hidden)
+    out = {}
+    for u in cols:
+        u = int(u)
+        s = lambda j: np.asarray(snap[(u + j) % K], dtype=float)
+
+        def dx(j):
+            k = (u + j) % K
+            xk = live[k] if (k in hid and k < u) else snap[k]
+            return D.dot(np.asarray(xk, dtype=float))
+        terms = {(u + 1) % K: (s(2) - s(-1), a - s(1), dx(1)),
+                 (u - 1) % K: (s(-2), a - s(-1) - s(-3) * s(-2), dx(-1)),
+                 (u + 2) % K: (-s(1), a + s(3) * s(1) - s(2), dx(2))}
+        r_uu = a + s(1) * s(-1) - s(-2) * s(-1)
+        lam = np.zeros(T)
+        rhs = np.zeros(T)
+        for k in sorted(set(list(terms.keys()) + [u])):       # ascending ODE index, as c(u) is sorted
+            if k == u:
+                rhs += W.T.dot(r_uu)
+            else:
+                Rv, rv, dxk = terms[k]
+                rhs += -Rv * (rv - dxk)
+                lam += Rv * Rv
+        out[u] = np.linalg.solve(M + np.diag(lam), rhs)
+    return out
+
+
 def lorenz96_state_cov(S, u, D, A):
     """Cov_u = (I+D)^T A (I+D) + A o sum_k R_k R_k^T  (closed form of proxies...py:239)."""
     T, K = S.shape

@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from variational_gradient_matching_for_dynamical_systems_b200 import OdeModel, build_host_plan
-from variational_gradient_matching_for_dynamical_systems_b200.distributed import HaloExchange, block_bounds, localize
+from variational_gradient_matching_for_dynamical_systems_b200.distributed import (HaloExchange, block_bounds, choose_shift,
+                                                                                   live_edges, localize, owned_states, owner_of)
 
 
 def _free_port():
@@ -170,5 +171,81 @@ def test_trajectory_batch_partition_has_no_halo_gloo_world2(tmp_path):
     world = 2
     port = _free_port()
     mp.spawn(_batch_worker, args=(world, port, 6, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d.txt" % r)).read() == "ok"
+
+
+@pytest.mark.parametrize("K,world", [(84, 3), (120, 4), (100000, 8)])
+def test_shifted_blocks_keep_the_wrap_around_read_on_one_rank(K, world):
+    """Lorenz96 with every second state observed has ONE live read, x_1 -> x_{K-1} (proxies...py:225); moving the
+    blocks two states up the ring puts both on the last rank, so no rank waits for another between levels, and that
+    rank's local plan keeps the tail-overlap tables (early = x_1, tail = x_{K-1})."""
+    model = OdeModel.lorenz96(K)
+    hidden = list(range(1, K, 2))
+    hp = build_host_plan(model, hidden)
+    src, dst = live_edges(hp)
+    assert src.tolist() == [1] and dst.tolist() == [K - 1]
+    assert hp.n_early == 1 and hp.slot_state[hp.early_slots].tolist() == [1]
+    assert len(hp.bulk_slots) == hp.level_ptr[1] - 1 and 0 not in hp.bulk_slots.tolist()
+    bounds = block_bounds(K, world, align=2)
+    assert choose_shift(hp, bounds, K, align=2) == 2
+    assert owner_of([1, K - 1, 2, 0], bounds, K, 2).tolist() == [world - 1, world - 1, 0, world - 1]
+    seen, hidden_seen = [], []
+    for r in range(world):
+        own = owned_states(bounds, r, K, 2)
+        loc = localize(model, hp, bounds[r], bounds[r + 1], owned=own)
+        assert np.array_equal(loc.owned, own) and loc.n_owned == len(own)
+        rows = np.concatenate([loc.owned, loc.halo_states])
+        assert np.array_equal(loc.row_map[rows], np.arange(len(rows)))
+        assert len(loc.halo_states) <= 6
+        lp = loc.plan
+        hidden_seen += rows[lp.slot_state].tolist()
+        seen += own.tolist()
+        if r == world - 1:
+            assert lp.n_early == 1 and rows[lp.slot_state[lp.early_slots]].tolist() == [1]
+            assert rows[lp.slot_state[lp.level_slots[lp.level_ptr[1]:]]].tolist() == [K - 1]
+            assert sorted(lp.bulk_slots.tolist() + lp.early_slots.tolist()) == sorted(lp.level_slots[:lp.level_ptr[1]].tolist())
+            # the live read is local: its source row is an OWNED row
+            assert lp.n_live == 1 and lp.live_state[0] < loc.n_owned
+        else:
+            assert lp.n_early == 0 and lp.n_live_pairs == 0 and lp.level_ptr[1] == lp.n_hidden
+    assert sorted(seen) == list(range(K)) and sorted(hidden_seen) == hidden
+
+
+def test_all_hidden_chain_has_no_tail_tables_and_no_good_shift():
+    K = 16
+    hp = build_host_plan(OdeModel.lorenz96(K), list(range(K)))
+    assert hp.n_early == 0 and hp.n_levels > 8
+    assert choose_shift(hp, block_bounds(K, 2, align=2), K, align=2) is None
+
+
+def _shift_worker(rank, world, port, K, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = OdeModel.lorenz96(K)
+        hp = build_host_plan(model, list(range(1, K, 2)))
+        bounds = block_bounds(K, world, align=2)
+        sh = choose_shift(hp, bounds, K, align=2)
+        loc = localize(model, hp, bounds[rank], bounds[rank + 1], owned=owned_states(bounds, rank, K, sh))
+        hx = HaloExchange(loc, bounds, shift=sh, K=K)
+        Xg = torch.arange(K * 5, dtype=torch.float64).reshape(K, 5) + 0.25
+        X = torch.zeros((loc.n_rows, 5), dtype=torch.float64)
+        X[:loc.n_owned] = Xg[torch.as_tensor(loc.owned)]
+        hx(X)
+        rows = np.concatenate([loc.owned, loc.halo_states])
+        ok = sh == 2 and bool(torch.equal(X, Xg[torch.as_tensor(rows)]))
+        with open(os.path.join(outdir, "rank%d.txt" % rank), "w") as f:
+            f.write("ok" if ok else "bad")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_halo_exchange_with_shifted_blocks_gloo_world2(tmp_path):
+    world, K = 2, 20
+    port = _free_port()
+    mp.spawn(_shift_worker, args=(world, port, K, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d.txt" % r)).read() == "ok"

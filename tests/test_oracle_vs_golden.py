@@ -179,3 +179,24 @@ def test_oracle_vs_live_reference_lorenz96():
                                                   None, None, obs, None, sc, 5, True, None, 'analytical')
     assert relerr(vo.lorenz96_theta_step(X0, Dr, Ar)[0], th.values.ravel()[0]) < 1e-13
     assert relerr(vo.lorenz96_state_sweep(X0, 8.0, Dr, list(range(1, K, 2))), out.values) < 1e-11
+
+
+@pytest.mark.parametrize("K,every_second", [(12, True), (9, False)])
+def test_sampled_columns_restatement_equals_full_sweep(K, every_second):
+    """lorenz96_sweep_columns (the C5 checker: a few hidden columns + the rows they read) gives the same columns as
+    the full sequential sweep, including the wrap-around state that reads x_1 live and an all-hidden chain."""
+    T = 60
+    t, X = vo.lorenz96_trajectory(K, T, 0.05, seed=2)
+    X0 = X + 0.3 * np.random.default_rng(3).standard_normal(X.shape)
+    D, *_ = vo.kernel_function(t, t[:2], "rbf", [0.0625, 1.0])
+    hidden = list(range(1, K, 2)) if every_second else list(range(K))
+    full = vo.lorenz96_state_sweep(X0, 8.0, D, hidden)
+    cols = hidden
+    need_s, need_l = vo.lorenz96_column_needs(cols, K, hidden)
+    if every_second:
+        assert need_l == [1]                       # only the wrap-around state K-1 reads an updated column
+    snap = {k: X0[:, k] for k in need_s}
+    live = {k: full[:, k] for k in need_l}
+    got = vo.lorenz96_sweep_columns(snap, live, K, 8.0, D, cols, hidden)
+    for u in cols:
+        assert relerr(got[u], full[:, u]) < 1e-12, u

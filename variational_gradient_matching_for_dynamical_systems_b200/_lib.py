@@ -53,7 +53,8 @@ class SweepPlan(C.Structure):
                 ("n_live", C.c_int), ("live_state", c_ip), ("live_level_ptr_host", C.POINTER(C.c_int)),
                 ("n_live_pairs", C.c_int), ("live_pair_slot", c_ip), ("live_pair_src", c_ip),
                 ("live_pair_level_ptr_host", C.POINTER(C.c_int)),
-                ("ruu_const", C.c_int), ("ruu_value", C.c_double)]
+                ("ruu_const", C.c_int), ("ruu_value", C.c_double),
+                ("n_early", C.c_int), ("early_slots", c_ip), ("bulk_slots", c_ip)]
 
 
 class Operators(C.Structure):
@@ -125,6 +126,8 @@ SIGNATURES = {
                                           _P(SweepInfo), C.c_void_p]),
     "vgm_state_sweep_level": (C.c_int, [_P(SweepPlan), _P(Operators), _P(SolverOpts), c_dp, C.c_int, c_dp, C.c_size_t,
                                         _P(SweepInfo), C.c_void_p]),
+    "vgm_state_sweep_levels": (C.c_int, [_P(SweepPlan), _P(Operators), _P(SolverOpts), c_dp, c_dp, C.c_size_t,
+                                         _P(SweepInfo), C.c_void_p]),
     "vgm_state_assemble": (C.c_int, [C.c_void_p, _P(SweepPlan), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                      C.c_void_p]),
     "vgm_pcg_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -29,7 +29,8 @@ import sympy as sym
 
 from . import _lib
 
-_IDENT = re.compile(r"[A-Za-z_][A-Za-z_0-9]*")
+# identifiers, but not the exponent of a numeric literal ("1e2" must not be read as the state name "e2")
+_IDENT = re.compile(r"(?<![0-9.])[A-Za-z_][A-Za-z_0-9]*")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _TEMPLATE = os.path.join(_HERE, "csrc", "vgm_program_template.cuh")
 
@@ -84,18 +85,29 @@ class OdeClass:
         self.present = [s in expr.free_symbols for s in placeholders]
         ex = expr.expand()                                         # rewrite...py:45,108
         # ---- linear in the parameters --------------------------------------------------
+        # A right-hand side that is NOT linear in a parameter (Protein Transduction: 1/(_K_m + _R_pp),
+        # FitzHugh-Nagumo: /_tau) still imports, has couplings and a state rewrite in the reference; only its
+        # parameter rewrite raises (rewrite...py:45).  Same here: the error is kept and raised by the parameter
+        # rewrite / the theta statistics, everything else works (state sweep with theta_mode='proxy').
         one = sym.Integer(1)
-        eB, eb = sym.linear_eq_to_matrix([ex], list(param_symbols))
-        eb = -eb
-        self.B, self.b = [], None
-        for e in list(eB):
+        self.param_nonlinear, self.param_error = False, None
+        self.B, self.b = [sym.Integer(0)] * len(param_symbols), sym.Integer(0)
+        try:
+            eB, eb = sym.linear_eq_to_matrix([ex], list(param_symbols))
+        except Exception as err:                                   # sympy NonlinearError
+            self.param_nonlinear, self.param_error = True, err
+            eB = None
+        if eB is not None:
+            eb = -eb
+            self.B = []
+            for e in list(eB):
+                if len(e.free_symbols) == 0:
+                    e = e if zero_fill else one                    # rewrite...py:49-50
+                self.B.append(e)
+            e = eb[0]
             if len(e.free_symbols) == 0:
-                e = e if zero_fill else one                        # rewrite...py:49-50
-            self.B.append(e)
-        e = eb[0]
-        if len(e.free_symbols) == 0:
-            e = e if zero_fill else one                            # rewrite...py:51-52
-        self.b = e
+                e = e if zero_fill else one                        # rewrite...py:51-52
+            self.b = e
         # ---- linear in each individual state ---------------------------------------------
         self.R, self.r, self.nonlinear = [], [], []
         for j, s in enumerate(placeholders):
@@ -166,6 +178,17 @@ class OdeModel:
         self._arity_of = np.array([c.arity for c in self.classes], dtype=np.int32)
         self._pairs = None
 
+    @property
+    def param_nonlinear(self):
+        """True if some right-hand side is not linear in the ODE parameters (no closed-form theta update)."""
+        return any(c.param_nonlinear for c in self.classes)
+
+    def require_linear_in_parameters(self):
+        """Raise what the reference's parameter rewrite raises (rewrite...py:45) for such a model."""
+        for c in self.classes:
+            if c.param_nonlinear:
+                raise c.param_error
+
     # ---- construction helpers -----------------------------------------------------------
     @classmethod
     def from_file(cls, path, state_names, param_names, **kw):
@@ -225,6 +248,10 @@ class OdeModel:
         for ci, c in enumerate(self.classes):
             subs = {ph: sym.Symbol("s[%d]" % j) for j, ph in enumerate(c.placeholders)}
             out.append("    case %d: {" % ci)
+            if c.param_nonlinear:                  # never evaluated: the host refuses the theta statistics
+                out.append("      for (int i = 0; i < VGM_NPARAM; ++i) B[i] = 0.0; b = 0.0;")
+                out.append("    } break;")
+                continue
             for i, e in enumerate(c.B):
                 out.append("      B[%d] = %s;" % (i, _ccode(e, subs)))
             out.append("      b = %s;" % _ccode(c.b, subs))
@@ -460,7 +487,32 @@ def build_host_plan(model: OdeModel, hidden, couplings=None, schedule="reference
     hp.live_pair_src = live_pair_src
     hp.live_pair_level_ptr = live_pair_level_ptr
     hp.ruu_const, hp.ruu_value = ruu_const, ruu_value
+    hp.n_early, hp.early_slots, hp.bulk_slots = tail_overlap_tables(nh, n_levels, level, level_ptr, prod_slots)
     return hp
+
+
+TAIL_MAX_SYSTEMS = 8     # csrc/small_solve.cuh: SMALL_SOLVE_MAX_SYSTEMS
+
+
+def tail_overlap_tables(nh, n_levels, level, level_ptr, prod_slots):
+    """When everything after dependency level 0 is a handful of systems (Lorenz96 with every second state observed:
+    the wrap-around state alone, which reads the updated x of the first hidden state, proxies...py:225), the sweep
+    can solve that chain on a side stream while the bulk of level 0 runs: the level-0 systems the chain reads live
+    (``early_slots``) are taken out of the bulk (``bulk_slots`` = the other level-0 slots) and solved first.
+    Returns (n_early, early_slots, bulk_slots); n_early = 0 when the plan does not have that shape."""
+    none = (0, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+    if n_levels < 2 or n_levels > TAIL_MAX_SYSTEMS:
+        return none
+    n_l0 = int(level_ptr[1])
+    if nh - n_l0 > TAIL_MAX_SYSTEMS or n_l0 <= 4 * TAIL_MAX_SYSTEMS:
+        return none
+    prod_slots = np.asarray(prod_slots, dtype=np.int64)
+    early = np.sort(prod_slots[level[prod_slots] == 0]) if len(prod_slots) else prod_slots
+    if len(early) == 0 or len(early) > TAIL_MAX_SYSTEMS:
+        return none
+    lvl0 = np.nonzero(level == 0)[0]
+    bulk = np.setdiff1d(lvl0, early)
+    return len(early), early.astype(np.int32), bulk.astype(np.int32)
 
 
 def colour_states(model, hidden, uu, kk, slot, prod, cand):

@@ -821,6 +821,7 @@ static int pcg_solve(const vgm_operators* ops, int ruu_const, const double* Ruu,
 // ------------------------------------------------------------------------------------
 struct SweepWs {
   double *Lambda, *rhs, *ruu, *Ruu, *Rlive, *DXlive;
+  double* tail_rhs;  // [SMALL_SOLVE_MAX_SYSTEMS][ld] right-hand sides of the tail systems before the live terms
   int* ident;  // identity row map for the live buffer
   PcgWs pcg;
 };
@@ -829,7 +830,8 @@ static size_t sweep_ws_bytes(const vgm_sweep_plan* pl) {
   const size_t mat = align_up((size_t)pl->n_hidden * pl->ld * sizeof(double), 256);
   const size_t live_pairs = align_up((size_t)max(pl->n_live_pairs, 1) * pl->ld * sizeof(double), 256);
   const size_t live = align_up((size_t)max(pl->n_live, 1) * pl->ld * sizeof(double), 256);
-  return (pl->ruu_const ? 3 : 4) * mat + live_pairs + live + pcg_ws_bytes(pl->n_hidden, pl->T, pl->ld) + 512;
+  const size_t tail = align_up((size_t)SMALL_SOLVE_MAX_SYSTEMS * pl->ld * sizeof(double), 256);
+  return (pl->ruu_const ? 3 : 4) * mat + live_pairs + live + tail + pcg_ws_bytes(pl->n_hidden, pl->T, pl->ld) + 512;
 }
 
 static int sweep_carve(void* ws, size_t ws_bytes, const vgm_sweep_plan* pl, SweepWs& w) {
@@ -849,6 +851,7 @@ static int sweep_carve(void* ws, size_t ws_bytes, const vgm_sweep_plan* pl, Swee
   }
   w.Rlive = (double*)p; p += live_pairs;
   w.DXlive = (double*)p; p += live;
+  w.tail_rhs = (double*)p; p += align_up((size_t)SMALL_SOLVE_MAX_SYSTEMS * pl->ld * sizeof(double), 256);
   const size_t used = (size_t)(p - (char*)ws);
   return pcg_carve(p, ws_bytes - used, pl->n_hidden, pl->T, pl->ld, w.pcg);
 }
@@ -994,16 +997,154 @@ int state_sweep_level_full(const vgm_sweep_plan* pl, const vgm_operators* ops, c
   return state_sweep_level(pl, ops, opts, X, lev, ws, ws_bytes, info, s);
 }
 
-static int state_sweep(const vgm_program* prog, const vgm_sweep_plan* pl, const vgm_operators* ops,
-                       const vgm_solver_opts* opts, double* X, const double* DX0, const double* theta_star, void* ws,
-                       size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
-  VGM_TRY(state_sweep_prepare(prog, pl, ops, X, DX0, theta_star, ws, ws_bytes, info, s));
+// ---- tail overlap (vgm_sweep_plan.n_early) ------------------------------------------------------------------
+// dst[i] = src[slot rows[i]] (save) or src[i] -> dst[slot rows[i]] (restore) for a handful of rows
+__global__ void tail_rows_copy_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                      const int* __restrict__ rows, int T, int ld, int restore) {
+  const size_t a = (size_t)rows[blockIdx.x] * ld, b = (size_t)blockIdx.x * ld;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    if (restore) dst[a + t] = src[b + t]; else dst[b + t] = src[a + t];
+  }
+}
+
+struct TailAsync {              // created once per process (one process drives one GPU)
+  cudaStream_t side = nullptr;  // highest priority: its single-CTA kernels are scheduled ahead of the bulk's CTAs
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int* status_host = nullptr;   // pinned, 64 ints
+};
+static TailAsync g_tail;
+static int tail_async_init() {
+  TailAsync& a = g_tail;
+  if (a.side) return VGM_OK;
+  int lo = 0, hi = 0;
+  VGM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  VGM_CUDA_OK(cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, hi));
+  VGM_CUDA_OK(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+  VGM_CUDA_OK(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+  VGM_CUDA_OK(cudaHostAlloc((void**)&a.status_host, 64 * sizeof(int), cudaHostAllocDefault));
+  return VGM_OK;
+}
+
+static bool tail_overlap_ok(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts) {
+  static const bool off = getenv("VGM_NO_TAIL_OVERLAP") != nullptr;
+  if (off || pl->n_early <= 0 || !pl->early_slots || !pl->bulk_slots || pl->n_levels < 2 ||
+      pl->n_levels > SMALL_SOLVE_MAX_SYSTEMS || pl->n_early > SMALL_SOLVE_MAX_SYSTEMS)
+    return false;
+  const int n_l0 = pl->level_ptr_host[1], n_tail = pl->n_hidden - n_l0;
+  if (n_tail <= 0 || n_tail > SMALL_SOLVE_MAX_SYSTEMS || n_l0 - pl->n_early <= SMALL_SOLVE_MAX_SYSTEMS) return false;
+  // same preconditions as the mixed-precision path whose tiny levels the single-CTA solver replaces
+  if (!ops->M_bf16x2 || !ops->G_bf16 || dense_solve_applicable(ops, pl->ruu_const, pl->T)) return false;
+  (void)opts;
+  return small_solve_applicable(ops, pl->ruu_const, max(pl->n_early, 1), pl->T);
+}
+
+// All levels, with the chain "early level-0 systems -> level 1 -> ..." on a side stream (one single-CTA launch per
+// link, nothing the host has to wait for) while the rest of level 0 is solved as one batch on `s`.
+static int state_sweep_levels_overlapped(const vgm_sweep_plan* pl, const vgm_operators* ops,
+                                         const vgm_solver_opts* opts, double* X, void* ws, size_t ws_bytes,
+                                         vgm_sweep_info* info, cudaStream_t s) {
+  SweepWs w;
+  VGM_TRY(sweep_carve(ws, ws_bytes, pl, w));
+  VGM_TRY(tail_async_init());
+  TailAsync& ta = g_tail;
+  const int T = pl->T, ld = pl->ld;
+  const int n_l0 = pl->level_ptr_host[1], n_tail = pl->n_hidden - n_l0, n_bulk = n_l0 - pl->n_early;
+  const int* tail_rows = pl->level_slots + n_l0;
+  Counters cnt;
+  VGM_CUDA_OK(cudaEventRecord(ta.fork, s));
+  VGM_CUDA_OK(cudaStreamWaitEvent(ta.side, ta.fork, 0));
+  cudaStream_t q = ta.side;
+  // the live terms are ADDED to rhs: keep the untouched right-hand sides for a clean fallback
+  tail_rows_copy_kernel<<<n_tail, row_threads(T), 0, q>>>(w.rhs, w.tail_rhs, tail_rows, T, ld, 0);
+  VGM_LAUNCH_OK();
+  SmallSolveArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.M = ops->M; sa.T = T; sa.ld = ld; sa.band_M = ops->band_M;
+  sa.Lambda = w.Lambda; sa.rhs = w.rhs; sa.X = X; sa.slot_state = pl->slot_state; sa.slot_has_self = pl->slot_has_self;
+  sa.Lscratch = w.pcg.small_scratch;
+  sa.tol = (opts && opts->tol > 0) ? opts->tol : 1e-13;
+  sa.max_pass = 8;
+  sa.done = w.pcg.cb.done; sa.iters = w.pcg.cb.iters;
+  int* status_dev = (int*)((char*)w.pcg.small_scratch + small_solve_scratch_bytes(T) - 256);   // 64 ints
+  VGM_CUDA_OK(cudaMemsetAsync(status_dev, 0, 64 * sizeof(int), q));
+  sa.rows = pl->early_slots; sa.status = status_dev;
+  VGM_TRY(small_solve(sa, pl->n_early, q));
+  cnt.launches += 3;
+  for (int lev = 1; lev < pl->n_levels; ++lev) {
+    const int l0 = pl->live_level_ptr_host[lev - 1], l1 = pl->live_level_ptr_host[lev];
+    if (l1 > l0) {
+      vgm_gemm_args g;
+      memset(&g, 0, sizeof(g));
+      g.A = X; g.B = ops->D; g.C = w.DXlive + (size_t)l0 * ld;
+      g.lda = g.ldb = g.ldc = ld;
+      g.N = l1 - l0; g.M = T; g.K = T;
+      g.rowsA = pl->live_state + l0;
+      g.alpha = 1.0;
+      g.band = ops->band_D;
+      VGM_TRY(dgemm_nt(g, q));
+      cnt.gemm += 1; cnt.launches += 1;
+    }
+    const int q0 = pl->live_pair_level_ptr_host[lev], q1 = pl->live_pair_level_ptr_host[lev + 1];
+    if (q1 > q0) {
+      add_live_terms_kernel<<<q1 - q0, row_threads(T), 0, q>>>(pl->live_pair_slot, pl->live_pair_src, q0, w.Rlive,
+                                                               w.DXlive, T, ld, w.rhs);
+      VGM_LAUNCH_OK();
+      cnt.launches += 1;
+    }
+    const int r0 = pl->level_ptr_host[lev], r1 = pl->level_ptr_host[lev + 1];
+    if (r1 > r0) {
+      sa.rows = pl->level_slots + r0; sa.status = status_dev + SMALL_SOLVE_MAX_SYSTEMS * lev;
+      VGM_TRY(small_solve(sa, r1 - r0, q));
+      cnt.launches += 1;
+    }
+  }
+  VGM_CUDA_OK(cudaMemcpyAsync(ta.status_host, status_dev, 64 * sizeof(int), cudaMemcpyDeviceToHost, q));
+  VGM_CUDA_OK(cudaEventRecord(ta.join, q));
+  // the bulk of level 0 (polls the device while the chain runs beside it)
+  int rc = pcg_solve(ops, pl->ruu_const, w.Ruu, w.Lambda, w.rhs, X, pl->slot_state, pl->slot_has_self, pl->bulk_slots,
+                     n_bulk, pl->n_hidden, T, ld, opts, w.pcg, info, cnt, s);
+  if (rc != VGM_OK && rc != VGM_ENOTCONV) return rc;
+  VGM_CUDA_OK(cudaStreamWaitEvent(s, ta.join, 0));
+  VGM_CUDA_OK(cudaEventSynchronize(ta.join));
+  bool chain_ok = true;
+  for (int i = 0; i < 64; ++i) chain_ok = chain_ok && ta.status_host[i] == 0;
+  if (info) { info->gemm_calls += cnt.gemm; info->kernel_launches += cnt.launches; info->iterations = max(info->iterations, 1); }
+  if (chain_ok) return rc;
+  // the single-CTA solver gave up on a link (it leaves x untouched then): restore the tail's right-hand sides and
+  // run the chain through the batched solvers, level by level
+  if (g_debug) fprintf(stderr, "[vgm] tail overlap: single-CTA solver did not converge, batched solvers take over\n");
+  tail_rows_copy_kernel<<<n_tail, row_threads(T), 0, s>>>(w.tail_rhs, w.rhs, tail_rows, T, ld, 1);
+  VGM_LAUNCH_OK();
+  Counters c2;
+  int r = pcg_solve(ops, pl->ruu_const, w.Ruu, w.Lambda, w.rhs, X, pl->slot_state, pl->slot_has_self, pl->early_slots,
+                    pl->n_early, pl->n_hidden, T, ld, opts, w.pcg, info, c2, s);
+  if (info) { info->gemm_calls += c2.gemm; info->kernel_launches += c2.launches + 1; }
+  if (r == VGM_ENOTCONV) rc = r; else if (r != VGM_OK) return r;
+  for (int lev = 1; lev < pl->n_levels; ++lev) {
+    r = state_sweep_level(pl, ops, opts, X, lev, ws, ws_bytes, info, s);
+    if (r == VGM_ENOTCONV) rc = r; else if (r != VGM_OK) return r;
+  }
+  return rc;
+}
+
+static int state_sweep_levels(const vgm_sweep_plan* pl, const vgm_operators* ops, const vgm_solver_opts* opts,
+                              double* X, void* ws, size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+  VGM_REQUIRE(pl && ops && X, "null argument");
+  if (pl->n_hidden == 0) return VGM_OK;
+  if (tail_overlap_ok(pl, ops, opts)) return state_sweep_levels_overlapped(pl, ops, opts, X, ws, ws_bytes, info, s);
   int rc = VGM_OK;
   for (int lev = 0; lev < pl->n_levels; ++lev) {
     int r = state_sweep_level(pl, ops, opts, X, lev, ws, ws_bytes, info, s);
     if (r == VGM_ENOTCONV) rc = r; else if (r != VGM_OK) return r;
   }
   return rc;
+}
+
+static int state_sweep(const vgm_program* prog, const vgm_sweep_plan* pl, const vgm_operators* ops,
+                       const vgm_solver_opts* opts, double* X, const double* DX0, const double* theta_star, void* ws,
+                       size_t ws_bytes, vgm_sweep_info* info, cudaStream_t s) {
+  VGM_TRY(state_sweep_prepare(prog, pl, ops, X, DX0, theta_star, ws, ws_bytes, info, s));
+  return state_sweep_levels(pl, ops, opts, X, ws, ws_bytes, info, s);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1116,6 +1257,11 @@ extern "C" int vgm_state_sweep_level(const vgm_sweep_plan* plan, const vgm_opera
                                      double* X, int level, void* ws, size_t ws_bytes, vgm_sweep_info* info,
                                      vgm_stream_t stream) {
   return state_sweep_level(plan, ops, opts, X, level, ws, ws_bytes, info, (cudaStream_t)stream);
+}
+
+extern "C" int vgm_state_sweep_levels(const vgm_sweep_plan* plan, const vgm_operators* ops, const vgm_solver_opts* opts,
+                                      double* X, void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream) {
+  return state_sweep_levels(plan, ops, opts, X, ws, ws_bytes, info, (cudaStream_t)stream);
 }
 
 extern "C" size_t vgm_state_sweep_ws_bytes(const vgm_sweep_plan* plan) { return plan ? sweep_ws_bytes(plan) : 0; }

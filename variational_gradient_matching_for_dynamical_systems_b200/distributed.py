@@ -57,22 +57,62 @@ class Localized:
     """Result of :func:`localize` (everything a rank needs, all host-side NumPy)."""
 
 
-def localize(model: OdeModel, hp: HostPlan, k0: int, k1: int) -> Localized:
-    """Restrict a global model + sweep plan to the states [k0, k1) owned by one rank.
+def owned_states(bounds, rank, K, shift=0):
+    """States of rank ``rank``: the block [bounds[rank], bounds[rank+1]) moved ``shift`` states up the ring
+    (mod K), in local row order.  A shift keeps a live read that wraps around the ring (Lorenz96: the last
+    hidden state reads the updated first one, proxies...py:225) inside one rank."""
+    return (np.arange(bounds[rank], bounds[rank + 1], dtype=np.int64) + shift) % K
 
-    Local X rows: owned states first (local row = k - k0), then the halo states (ascending
+
+def owner_of(states, bounds, K, shift=0):
+    """Rank that owns each state under ``owned_states``."""
+    s = (np.asarray(states, dtype=np.int64) - shift) % K
+    return np.searchsorted(np.asarray(bounds), s, side="right") - 1
+
+
+def live_edges(hp: HostPlan):
+    """(source state, consumer state) of every live read of the plan: the consumer's system takes D.x of the
+    source from the column updated earlier in the same sweep (proxies...py:185,225)."""
+    if hp.n_live_pairs == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    slot_state = np.asarray(hp.slot_state, dtype=np.int64)
+    src = np.asarray(hp.live_state, dtype=np.int64)[np.asarray(hp.live_pair_src, dtype=np.int64)]
+    dst = slot_state[np.asarray(hp.live_pair_slot, dtype=np.int64)]
+    return src, dst
+
+
+def choose_shift(hp: HostPlan, bounds, K, align=1, max_tries=16):
+    """Smallest block shift (a multiple of ``align``) under which no live read crosses a rank boundary, or None.
+    Lorenz96 with every second state observed: the only live read is x_1 -> x_{K-1}; shift 2 puts both on the last
+    rank, so no rank waits for another between dependency levels."""
+    src, dst = live_edges(hp)
+    for i in range(max_tries):
+        sh = i * align
+        if len(src) == 0 or np.array_equal(owner_of(src, bounds, K, sh), owner_of(dst, bounds, K, sh)):
+            return sh
+    return None
+
+
+def localize(model: OdeModel, hp: HostPlan, k0: int, k1: int, owned=None) -> Localized:
+    """Restrict a global model + sweep plan to the states owned by one rank: [k0, k1), or the explicit list
+    ``owned`` (local row order; ``owned_states`` gives the cyclically shifted blocks).
+
+    Local X rows: owned states first (local row = position in ``owned``), then the halo states (ascending
     global index) that owned ODE rows / owned hidden states read.  Local ODE rows: owned ODEs
     first (they alone enter the theta statistics), then the neighbours' ODEs that couple to an
     owned hidden state (needed for R_uk, r_uk and D x_k of those pairs)."""
     K = model.K
+    owned = np.arange(k0, k1, dtype=np.int64) if owned is None else np.asarray(owned, dtype=np.int64)
+    is_owned = np.zeros(K, dtype=bool)
+    is_owned[owned] = True
     arity_of = np.array([c.arity for c in model.classes], dtype=np.int64)
     slot_state = np.asarray(hp.slot_state, dtype=np.int64)
-    loc_slots = np.nonzero((slot_state >= k0) & (slot_state < k1))[0]
+    loc_slots = np.nonzero(is_owned[slot_state])[0]
     slot_map = np.full(hp.n_hidden, -1, dtype=np.int64)
     slot_map[loc_slots] = np.arange(len(loc_slots))
     pair_slot = np.repeat(np.arange(hp.n_hidden), np.diff(hp.pair_ptr))
     pair_sel = np.nonzero(slot_map[pair_slot] >= 0)[0]
-    owned_odes = np.arange(k0, k1, dtype=np.int64)
+    owned_odes = owned.copy()
     extra_odes = np.setdiff1d(np.unique(hp.pair_ode[pair_sel]).astype(np.int64), owned_odes)
     odes = np.concatenate([owned_odes, extra_odes])
     ode_map = np.full(K, -1, dtype=np.int64)
@@ -85,15 +125,18 @@ def localize(model: OdeModel, hp: HostPlan, k0: int, k1: int) -> Localized:
     src_global_state = np.asarray(hp.live_state, dtype=np.int64)[hp.live_pair_src[hp.pair_live[live_e]]] \
         if len(live_e) else np.zeros(0, dtype=np.int64)
     needed = np.unique(np.concatenate([idx[valid], model.ode_state[odes].astype(np.int64), src_global_state]))
-    halo = needed[(needed < k0) | (needed >= k1)]
+    halo = needed[~is_owned[needed]]
+    n_owned = len(owned)
     row_map = np.full(K, -1, dtype=np.int64)
-    row_map[k0:k1] = np.arange(k1 - k0)
-    row_map[halo] = (k1 - k0) + np.arange(len(halo))
+    row_map[owned] = np.arange(n_owned)
+    row_map[halo] = n_owned + np.arange(len(halo))
     out = Localized()
     out.k0, out.k1 = k0, k1
-    out.n_owned = k1 - k0
+    out.owned = owned
+    out.row_map = row_map
+    out.n_owned = n_owned
     out.halo_states = halo
-    out.n_rows = (k1 - k0) + len(halo)
+    out.n_rows = n_owned + len(halo)
     out.ode_class = model.ode_class[odes].astype(np.int32)
     li = np.where(valid, row_map[idx], 0)
     assert (li >= 0).all()
@@ -151,6 +194,18 @@ def localize(model: OdeModel, hp: HostPlan, k0: int, k1: int) -> Localized:
         np.add.at(lpl, lp.level[consumer_slot_local] + 1, 1)
     lp.live_pair_level_ptr = np.cumsum(lpl).astype(np.int32)
     lp.ruu_const, lp.ruu_value = hp.ruu_const, hp.ruu_value
+    # tail overlap (codegen.tail_overlap_tables): usable on this rank only if it owns the whole chain, i.e. every
+    # early system of the global plan together with every system of the later levels
+    n_early = int(getattr(hp, "n_early", 0))
+    lp.n_early, lp.early_slots, lp.bulk_slots = 0, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32)
+    if n_early:
+        early_l = slot_map[np.asarray(hp.early_slots, dtype=np.int64)]
+        tail_g = np.nonzero(np.asarray(hp.level) > 0)[0]
+        if (early_l >= 0).all() and (slot_map[tail_g] >= 0).all():
+            lvl0 = np.nonzero(lp.level == 0)[0]
+            lp.n_early = n_early
+            lp.early_slots = np.sort(early_l).astype(np.int32)
+            lp.bulk_slots = np.setdiff1d(lvl0, early_l).astype(np.int32)
     out.plan = lp
     out.hidden_global = slot_state[loc_slots]
     return out
@@ -160,25 +215,25 @@ class HaloExchange:
     """Refresh of the halo rows of X: every rank contributes the owned rows that any other
     rank reads (padded to a common count) to one all-gather and then picks its halo rows."""
 
-    def __init__(self, loc: Localized, bounds, group=None):
+    def __init__(self, loc: Localized, bounds, group=None, shift=0, K=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         halos = [None] * self.world
         dist.all_gather_object(halos, loc.halo_states.tolist(), group=group)
         bounds = np.asarray(bounds)
+        K = int(bounds[-1]) if K is None else int(K)
         send = [[] for _ in range(self.world)]          # owned states each rank must publish
         for r, hs in enumerate(halos):
-            for s in hs:
-                owner = int(np.searchsorted(bounds, s, side="right") - 1)
+            for s, owner in zip(hs, owner_of(hs, bounds, K, shift).tolist() if len(hs) else []):
                 send[owner].append(int(s))
         send = [sorted(set(v)) for v in send]
         # trajectory batches: nobody reads anybody's rows, so there is no exchange at all (same answer on every rank)
         self.empty = all(len(v) == 0 for v in send)
         self.n_pub = max(1, max(len(v) for v in send))
-        self.pub_rows_local = np.array([s - loc.k0 for s in send[self.rank]], dtype=np.int64)
+        self.pub_rows_local = np.array([loc.row_map[s] for s in send[self.rank]], dtype=np.int64)
         pos = [{s: i for i, s in enumerate(v)} for v in send]
-        owners = [int(np.searchsorted(bounds, s, side="right") - 1) for s in loc.halo_states.tolist()]
+        owners = owner_of(loc.halo_states, bounds, K, shift).tolist() if len(loc.halo_states) else []
         self.src_flat = np.array([o * self.n_pub + pos[o][int(s)] for o, s in zip(owners, loc.halo_states.tolist())],
                                  dtype=np.int64)
         self.halo_rows_local = loc.n_owned + np.arange(len(loc.halo_states), dtype=np.int64)
@@ -213,7 +268,7 @@ class DistributedVGMEngine:
     TAIL_LEVEL_COST_STATES = 0
 
     def __init__(self, model: OdeModel, D, A=None, hidden=None, schedule="reference", align=2, group=None,
-                 tail_level_cost_states=None, **kw):
+                 tail_level_cost_states=None, shift="auto", **kw):
         from .engine import LocalProblem, VGMEngine
         self.group = group
         self.world = dist.get_world_size(group)
@@ -226,12 +281,22 @@ class DistributedVGMEngine:
         tail = self.TAIL_LEVEL_COST_STATES if tail_level_cost_states is None else tail_level_cost_states
         self.bounds = block_bounds(model.K, self.world, align=align,
                                    weights=state_weights(model, hp, tail) if tail > 0 else None)
+        # blocks are moved up the ring by `shift` states when that keeps every live read inside one rank: then no
+        # rank waits for another between dependency levels (and the tail overlap of the sweep stays available)
+        if shift == "auto":
+            sh = choose_shift(hp, self.bounds, model.K, align=align)
+            self.shift = 0 if sh is None else int(sh)
+        else:
+            self.shift = int(shift)
+        src, dst = live_edges(hp)
+        self.cross_rank_live = bool(len(src)) and not np.array_equal(owner_of(src, self.bounds, model.K, self.shift),
+                                                                     owner_of(dst, self.bounds, model.K, self.shift))
         k0, k1 = self.bounds[self.rank], self.bounds[self.rank + 1]
-        self.loc = localize(model, hp, k0, k1)
+        self.loc = localize(model, hp, k0, k1, owned=owned_states(self.bounds, self.rank, model.K, self.shift))
         prob = LocalProblem(self.loc.n_rows, self.loc.n_stats_odes, self.loc.ode_class, self.loc.ode_idx,
                             self.loc.ode_state, self.loc.plan, model.p)
         self.engine = VGMEngine(model, D, A, problem=prob, **kw)
-        self.halo = HaloExchange(self.loc, self.bounds, group=group)
+        self.halo = HaloExchange(self.loc, self.bounds, group=group, shift=self.shift, K=model.K)
         self.n_hidden_global = hp.n_hidden
         self.n_levels = hp.n_levels
 
@@ -239,26 +304,47 @@ class DistributedVGMEngine:
     def set_states_state_major(self, X_global_KT):
         """Every rank passes the same global [K, T] array (or at least its own block + halo)."""
         e, loc = self.engine, self.loc
-        rows = np.concatenate([np.arange(loc.k0, loc.k1), loc.halo_states]).astype(np.int64)
+        rows = np.concatenate([loc.owned, loc.halo_states]).astype(np.int64)
         Xg = torch.as_tensor(X_global_KT)
         idx = torch.as_tensor(rows, device=Xg.device)
         e.X.zero_()
         e.X[:, :e.T] = Xg.index_select(0, idx)[:, :e.T].to(e.dev, dtype=torch.float64)
 
     def owned_states(self):
-        """[n_owned, T] tensor of this rank's block."""
+        """[n_owned, T] tensor of this rank's block (local row order = ``self.loc.owned``)."""
         return self.engine.X[:self.loc.n_owned, :self.engine.T]
 
     def gather_states(self):
         """Global [K, T] tensor on every rank (for tests/reporting)."""
         e = self.engine
+        K = self.model.K
         sizes = [self.bounds[g + 1] - self.bounds[g] for g in range(self.world)]
         mx = max(sizes)
         mine = torch.zeros((mx, e.T), dtype=torch.float64, device=e.dev)
         mine[:self.loc.n_owned] = self.owned_states()
         allb = torch.zeros((self.world * mx, e.T), dtype=torch.float64, device=e.dev)
         dist.all_gather_into_tensor(allb, mine, group=self.group)
-        return torch.cat([allb[g * mx:g * mx + sizes[g]] for g in range(self.world)], 0)
+        out = torch.empty((K, e.T), dtype=torch.float64, device=e.dev)
+        for g in range(self.world):
+            idx = torch.as_tensor(owned_states(self.bounds, g, K, self.shift), device=e.dev)
+            out.index_copy_(0, idx, allb[g * mx:g * mx + sizes[g]])
+        return out
+
+    def gather_rows(self, states, source=None):
+        """[len(states), ld] tensor, on every rank, of the rows of the GLOBAL states ``states``: every rank
+        contributes the rows it owns (one all-reduce of a few rows; for parity checks and reporting).  ``source`` is
+        a local [n_rows, ld] tensor laid out like the engine's X (default: the engine's X)."""
+        e = self.engine
+        src = e.X if source is None else source
+        states = np.asarray(states, dtype=np.int64)
+        mine = owner_of(states, self.bounds, self.model.K, self.shift) == self.rank
+        out = torch.zeros((len(states), src.shape[1]), dtype=src.dtype, device=src.device)
+        if mine.any():
+            pos = torch.as_tensor(np.nonzero(mine)[0], device=src.device)
+            rows = torch.as_tensor(self.loc.row_map[states[mine]], device=src.device)
+            out.index_copy_(0, pos, src.index_select(0, rows))
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
 
     # ---- one coordinate-ascent iteration ---------------------------------------------------------------
     def iteration(self, allow_unconverged=False):
@@ -269,6 +355,10 @@ class DistributedVGMEngine:
         dist.all_reduce(e.stats, op=dist.ReduceOp.SUM, group=self.group)
         e.param_solve()
         e.sweep_prepare()
+        if not self.cross_rank_live:
+            # every live read stays on its rank: the levels run back to back, nobody waits for anybody
+            e.sweep_levels(allow_unconverged=allow_unconverged)
+            return e.last_info
         for lev in range(self.n_levels):
             if lev > 0:
                 self.halo(e.X)                           # rows updated by their owners in level lev-1

@@ -144,8 +144,8 @@ class DevicePlan:
         self.host = hp
         keep = self._keep = {}
         for name in ("slot_state", "pair_ptr", "pair_ode", "pair_code", "pair_live", "pair_self", "slot_has_self",
-                     "level_slots", "live_state", "live_pair_slot", "live_pair_src"):
-            arr = getattr(hp, name)
+                     "level_slots", "live_state", "live_pair_slot", "live_pair_src", "early_slots", "bulk_slots"):
+            arr = getattr(hp, name, np.zeros(0, dtype=np.int32))
             keep[name] = _i32(arr if len(arr) else np.zeros(1, dtype=np.int32), dev)
         for name in ("level_ptr", "live_level_ptr", "live_pair_level_ptr"):
             keep[name + "_host"] = _host_i32(getattr(hp, name))
@@ -171,6 +171,9 @@ class DevicePlan:
         p.live_pair_src = keep["live_pair_src"].data_ptr()
         p.live_pair_level_ptr_host = C.cast(keep["live_pair_level_ptr_host"], C.POINTER(C.c_int))
         p.ruu_const, p.ruu_value = hp.ruu_const, hp.ruu_value
+        p.n_early = int(getattr(hp, "n_early", 0))
+        p.early_slots = keep["early_slots"].data_ptr() if p.n_early else None
+        p.bulk_slots = keep["bulk_slots"].data_ptr() if p.n_early else None
         self.c = p
         self.n_hidden = hp.n_hidden
         self.hidden = np.asarray(hp.slot_state, dtype=np.int64)
@@ -418,6 +421,7 @@ class VGMEngine:
 
     def param_stats(self):
         """Sufficient statistics [m | S] of the theta update on the device."""
+        self.model.require_linear_in_parameters()
         n_odes = self.problem.n_stats_odes
         n = self.lib.vgm_param_stats_ws_bytes(n_odes, self.T, self.p)
         _lib.check(self.lib.vgm_param_stats(self.program.handle, self.X.data_ptr(), self.DX.data_ptr(), self.ld, self.T,
@@ -469,8 +473,18 @@ class VGMEngine:
         self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
         _lib.check(rc, allow_notconv=allow_unconverged)
 
+    def sweep_levels(self, allow_unconverged=False):
+        """Phase 2 of a sweep for every level in order (vgm_state_sweep_levels), tail overlap included."""
+        n = self.lib.vgm_state_sweep_ws_bytes(C.byref(self.plan.c))
+        rc = self.lib.vgm_state_sweep_levels(C.byref(self.plan.c), C.byref(self._cops), C.byref(self.opts),
+                                             self.X.data_ptr(), self.ws.data_ptr(), n, C.byref(self.info),
+                                             _lib.stream_ptr())
+        self.last_info = {k: getattr(self.info, k) for k, _ in _lib.SweepInfo._fields_}
+        _lib.check(rc, allow_notconv=allow_unconverged)
+
     def iteration(self, allow_unconverged=False):
         """theta update followed by the state sweep, all on the device (vgm_iteration_device)."""
+        self.model.require_linear_in_parameters()
         if self._cops.G is None and self.precondition and self.plan.c.ruu_const and self.plan.n_hidden:
             self.compute_DX()
             self._prepare_preconditioner()
@@ -500,6 +514,7 @@ class VGMEngine:
         ``pipeline_chunks`` >= 2: cut the states into that many ranges and overlap the host->device copy of range
         c+1 and the device->host copy of range c-1 with the solve of range c (falls back to the plain path when the
         model does not allow it; ``self.last_pipeline`` tells which ran)."""
+        self.model.require_linear_in_parameters()
         if X_host_out is None:
             X_host_out = X_host_KT
         pkey = pipeline_chunks if np.isscalar(pipeline_chunks) else tuple(pipeline_chunks)
@@ -543,6 +558,7 @@ class VGMEngine:
         drops it).  Evaluated on the current states."""
         if self.ops.A is None:
             raise ValueError("eps_cov (A) was not given")
+        self.model.require_linear_in_parameters()
         n_odes = self.problem.n_stats_odes
         n = self.lib.vgm_param_cov_ws_bytes(n_odes, self.ld, self.p)
         ws = torch.empty(n + 256, dtype=torch.uint8, device=self.dev)

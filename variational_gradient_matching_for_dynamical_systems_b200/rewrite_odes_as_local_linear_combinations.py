@@ -129,8 +129,7 @@ def rewrite_odes_as_linear_combination_in_parameters(odes, state_symbols, ode_pa
     original; the default reproduces the Python reference as written.'''
     state_symbols = list(state_symbols)            # never mutate the caller's list (rewrite...py:36)
     model = _model_from(odes, state_symbols, ode_param_symbols, zero_fill=zero_fill)
-    for c in model.classes:                        # surfaces NonlinearError-like problems early
-        assert len(c.B) == model.p
+    model.require_linear_in_parameters()           # sympy NonlinearError, as rewrite...py:45 raises it
     return ParamCoefficients(model, "B", state_symbols), ParamCoefficients(model, "b", state_symbols)
 
 
