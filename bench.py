@@ -61,6 +61,8 @@ def parse():
                          "of the ranges as fractions; a short first range starts the compute early, a short last "
                          "one shortens the final copy-out; 0 = no pipelining")
     ap.add_argument("--no-profile", action="store_true", help="skip the second, per-kernel-instrumented timed region")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 trajectory-batch block")
+    ap.add_argument("--c4-trajectories", type=int, default=65536)
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of sampled hidden columns + theta")
     ap.add_argument("--parity-columns", type=int, default=64)
     args = ap.parse_args()
@@ -196,6 +198,110 @@ def parity_block(args, eng, core, X0_local, world, rank, K, T, hidden, n_columns
     if world > 1:
         flag = torch.tensor([1 if (out is None or out["ok"]) else 0], device=core.X.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Config C4 (BASELINE.json configs[3]): 65 536 independent Protein-Transduction trajectories sharing one theta,
+# trajectories split across the ranks, ONE all-reduce of the pooled parameter statistics per iteration.
+# Model as in SURVEY.md 8d: K_m -> 0.3 so that the system is linear in the remaining 5 parameters; states S and RS are
+# hidden, dS, R, R_pp observed and clamped; T = 99.  Inputs: the golden single trajectory (generated from the live
+# reference set-up, tests/golden/protein_transduction_T99.npz) scaled per trajectory and state by 1 + 0.05 N(0,1).
+# ----------------------------------------------------------------------------------------------
+def c4_block(args, world, rank, dev):
+    import sympy as sym
+    import torch
+    import torch.distributed as dist
+    from oracle import vgm_oracle as vo
+    from variational_gradient_matching_for_dynamical_systems_b200 import OdeModel
+    from variational_gradient_matching_for_dynamical_systems_b200.engine import VGMEngine
+    t_all = time.perf_counter()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "protein_transduction_T99.npz"))
+    lines, params, names = [str(x) for x in g["lines"]], [str(x) for x in g["params"]], [str(x) for x in g["names"]]
+    sc = [[int(v) for v in str(c).split(",") if v != ""] for c in g["couplings"]]
+    observed = [str(x) for x in g["observed"]]
+    K1, T, N = len(names), g["X0"].shape[0], args.c4_trajectories
+    hidden1 = [u for u in range(K1) if names[u] not in observed]
+    D, A = g["D"], g["A"]
+    rng = np.random.default_rng(7)
+    scale = 1.0 + 0.05 * rng.standard_normal((N, 1, K1))
+    Xn = g["X0"][None, :, :] * scale                                   # [N, T, K1]
+    X_KT = np.ascontiguousarray(Xn.transpose(0, 2, 1).reshape(N * K1, T))   # state-major, trajectory n = rows n*K1..
+    model = OdeModel(lines, names, params, n_copies=N)
+    hidden = np.array([n * K1 + u for n in range(N) for u in hidden1])
+    t0 = time.perf_counter()
+    if world > 1:
+        from variational_gradient_matching_for_dynamical_systems_b200.distributed import DistributedVGMEngine
+        eng = DistributedVGMEngine(model, D, A, hidden=hidden, align=K1, theta_mode="proxy")
+        core = eng.engine
+    else:
+        eng = core = VGMEngine(model, D, A, hidden=hidden, couplings=sc, theta_mode="proxy")
+    eng.set_states_state_major(torch.as_tensor(X_KT))
+    X0_local = core.X.clone()
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    def step():
+        core.X.copy_(X0_local)
+        return eng.iteration()
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n_it = max(3, args.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_it):
+        info = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_it
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    # ---- parity: pooled statistics / theta vs a vectorised NumPy restatement of proxies...py:58-93 (trajectories are
+    # just more rows of the sums), and a few trajectories' sweeps vs oracle.state_sweep (proxies...py:195-262)
+    theta_gpu = core.get_theta()
+    stats_gpu = core.stats.cpu().numpy()
+    pick = sorted(rng.choice(N, size=min(8, N), replace=False).tolist())
+    rows = np.array([n * K1 + u for n in pick for u in range(K1)])
+    if world > 1:
+        got = eng.gather_rows(rows)[:, :T].cpu().numpy()
+    else:
+        got = core.X.index_select(0, torch.as_tensor(rows, device=dev))[:, :T].cpu().numpy()
+    out = None
+    if rank == 0:
+        lin = vo.Linearisation(vo.parse_ode_lines(lines), sym.symbols(names), sym.symbols(params), couplings=sc)
+        S_big = Xn.reshape(N * T, K1)
+        DX_big = np.einsum("st,ntk->nsk", D, Xn).reshape(N * T, K1)
+        m, Sc = np.zeros(lin.p), np.zeros((lin.p, lin.p))
+        for k in range(K1):
+            B, b = lin.eval_B_b(k, S_big)
+            m += B.T.dot(DX_big[:, k] - b)
+            Sc += B.T.dot(B)
+        theta_ref = np.linalg.solve(Sc, m)
+        rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+        worst = 0.0
+        for i, n in enumerate(pick):
+            Xr, _ = vo.state_sweep(Xn[n], theta_ref, lin, D, hidden1)          # [T, K1]
+            worst = max(worst, rel(got[i * K1:(i + 1) * K1].T, Xr))
+        par = {"rel_local_mean": rel(stats_gpu[:lin.p], m), "rel_local_scaling": rel(stats_gpu[lin.p:].reshape(lin.p, lin.p), Sc),
+               "rel_theta": rel(theta_gpu, theta_ref), "max_rel_states_sampled": worst, "sampled_trajectories": len(pick),
+               "tol": PARITY_TOL}
+        par["ok"] = bool(max(par["rel_local_mean"], par["rel_local_scaling"], par["rel_theta"], worst) < PARITY_TOL)
+        out = {"workload": "C4: %d Protein-Transduction trajectories (K_m -> 0.3: 5 states, 5 shared parameters), T=%d, "
+                           "hidden S and RS; trajectories split over %d GPU(s), one all-reduce of p + p^2 = %d "
+                           "statistics per iteration" % (N, T, world, lin.p + lin.p ** 2),
+               "n_trajectories": N, "n_gpus": world, "hidden_systems": int(len(hidden)), "iterations_timed": n_it,
+               "ms_per_iteration": ms, "trajectories_per_s": N / (ms * 1e-3),
+               "state_time_updates_per_s": len(hidden) * T / (ms * 1e-3), "solver": core.solver,
+               "solver_info": dict(info) if isinstance(info, dict) else None, "setup_s": round(setup_s, 2),
+               "parity": par, "seconds": round(time.perf_counter() - t_all, 2)}
+    del eng, core, X0_local
+    torch.cuda.empty_cache()
     return out
 
 
@@ -410,6 +516,11 @@ def native_arm(args):
     if not args.no_parity:
         parity = parity_block(args, eng, core, X0_local, world, rank, K, T, hidden, args.parity_columns)
 
+    # ---- config C4 under the same launch (trajectory batch + all-reduce of the pooled statistics) ------------
+    c4 = None
+    if not args.no_c4:
+        c4 = c4_block(args, world, rank, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -490,7 +601,7 @@ def native_arm(args):
                        "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
                              (n_hidden_local * core.ld * 8 / 1e6),
                        "profiled_ms_per_step": (ms_prof / args.steps) if ms_prof else None},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "c4": c4, "gpu_launches": launches,
             "clocks": clocks,
             "solver_iterations": pcg_iters, "theta": theta, "setup_s": setup_s,
             "evolving_loop": evolving,
@@ -502,6 +613,9 @@ def native_arm(args):
         dist.destroy_process_group()
     if parity is not None and not parity["ok"]:
         sys.stderr.write("bench.py: PARITY FAILURE against the oracle: %r\n" % (parity,))
+        return 3
+    if c4 is not None and not c4["parity"]["ok"]:
+        sys.stderr.write("bench.py: C4 PARITY FAILURE against the oracle: %r\n" % (c4["parity"],))
         return 3
     return 0
 

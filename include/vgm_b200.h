@@ -15,7 +15,11 @@
  *     workspace pointers sized by the matching *_ws_bytes() function;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); only the functions
  *     documented as synchronising (they return host scalars) wait for the device;
- *   - there is no CPU fallback anywhere in this library.
+ *   - there is no CPU fallback anywhere in this library;
+ *   - ONE PROCESS DRIVES ONE GPU: the library keeps a few process-wide resources (internal streams and events,
+ *     cached CUDA graphs of the correction sequence, kernel attributes) that belong to the device it was first
+ *     used on; the sweep / iteration entry points return VGM_EINVAL when called with another current device, and
+ *     they are not re-entrant (call them from one thread at a time).  vgm_shutdown() drops the cached graphs.
  */
 #ifndef VGM_B200_H
 #define VGM_B200_H
@@ -40,6 +44,7 @@ enum {
 
 const char* vgm_last_error(void);
 int vgm_version(void);
+int vgm_shutdown(void); /* drop cached CUDA graphs (they point into caller workspaces) and the device binding */
 
 /* ------------------------------------------------------------------------------------
  * G1  GP_regression.kernel_function, GP_regression.py:160-260
@@ -142,6 +147,20 @@ int vgm_gm_operators_lu(const double* C, const double* dC, const double* ddC, in
 int vgm_spd_inverse(const double* S, int T, int ld, double* Sinv, void* ws, size_t ws_bytes, vgm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * F1  GP_regression.fitting_state_observations, GP_regression.py:33-51 (the initial state proxy)
+ *   for observed state i (in column order):  cov_obs += sigma_i^2 I   (the reference REASSIGNS cov_obs inside its
+ *   loop, :42, so state i sees the noise of all states before it);  mean_i = Cso solve(cov_obs, y_i)        (:43)
+ *   pred_cov = cov - Cso solve(cov_obs, Cso^T) with the final accumulated cov_obs                            (:45)
+ * Cholesky solves (no explicit inverse) + DMMA GEMMs.  Cobs [T2][ld2], Cso [T][ld2], C [T][ld] (may be null when
+ * pred_cov is null), Y [n_obs][ld2] (one observed state's series per row), obs_var_host [n_obs] = sigma_i^2 on the
+ * HOST; outputs mean [n_obs][ld], pred_cov [T][ld] (optional).  Synchronises the stream (pivot checks);
+ * VGM_ENOTSPD if cov_obs is not numerically positive definite. */
+size_t vgm_gp_fit_ws_bytes(int T, int T2, int ld2);
+int vgm_gp_fit(const double* Cobs, const double* Cso, const double* C, int T, int T2, int ld, int ld2, const double* Y,
+               const double* obs_var_host, int n_obs, double* mean, double* pred_cov, void* ws, size_t ws_bytes,
+               vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * G3/G4  rewrite_odes_as_local_linear_combinations.py:28-58,76-124
  * A "program" holds the model-specific coefficient kernels (B_k, b_k per ODE; R_uk, r_uk per
  * state x ODE) generated from the SymPy rewrite as CUDA device functions.  Programs are
@@ -236,6 +255,10 @@ typedef struct {
   const double* DtD;    /* optional D^T D, [T][ld]: with T <= 160 it enables the direct per-CTA solver for systems
                            whose R_uu varies in time (each CTA forms D^T D - diag(R) D - D^T diag(R) +
                            diag(R^2 + Lambda) in shared memory and factorises it); constant R_uu uses M          */
+  const double* obs_rhs; /* optional observation term (opt-in; the statement the reference keeps commented out at
+                           proxies...py:265-266, active in the MATLAB original, proxy_for_ind_states.m:92-93):
+                           x_u = solve(local_scaling + Q, local_mean + Q mu_u) with Q = state_pred_inv_cov.  The
+                           caller adds Q to M (or to DtD) and passes obs_rhs[slot] = Q mu_u, [n_hidden][ld]      */
 } vgm_operators;
 int vgm_convert_bf16(const double* in, void* out_bf16, int rows, int ld, vgm_stream_t stream);
 int vgm_split_bf16(const double* in, void* out_bf16x2, int rows, int ld, vgm_stream_t stream);

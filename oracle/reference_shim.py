@@ -155,6 +155,20 @@ def load_reference():
     patched.__file__ = src_path
     exec(compile(src.replace(needle, "                pass\n"), src_path, "exec"), patched.__dict__)
     ns.proxies_patched = patched
+    # observation-term variant: the reference's OWN commented-out statement (:265-266) put in the place of the
+    # active solve (:262); nothing else changes (the literal [8] stays, so it serves one-parameter models)
+    active = "                global_mean[:,u] = np.squeeze(np.linalg.solve(local_scaling,local_mean)) \n"
+    commented = ("#                global_mean[:,u] = np.squeeze(np.linalg.solve(local_scaling + state_pred_inv_cov,\\\n"
+                 "#                           local_mean + np.dot(state_pred_inv_cov,state_pred_mean.iloc[:,u])))\n")
+    if src.count(active) == 1 and src.count(commented) >= 1:
+        stmt = ("                global_mean[:,u] = np.squeeze(np.linalg.solve(local_scaling + state_pred_inv_cov,"
+                "local_mean + np.dot(state_pred_inv_cov,state_pred_mean.iloc[:,u])))\n")
+        obs = types.ModuleType("proxies_for_ode_parameters_and_states_obs_term")
+        obs.__file__ = src_path
+        exec(compile(src.replace(active, stmt), src_path, "exec"), obs.__dict__)
+        ns.proxies_obs_term = obs
+    else:
+        ns.proxies_obs_term = None
     _CACHE["ns"] = ns
     return ns
 

@@ -151,6 +151,14 @@ def fit_state_observations(obs_values, obs_cols, n_states, SNR, cov, cov_obs, co
     return mean, np.linalg.pinv(pred_cov)
 
 
+def predictive_cov(obs_values, SNR, cov, cov_obs, cov_state_obs):
+    """``state_pred_cov`` of GP_regression.py:45 (the matrix whose pinv the function returns)."""
+    obs_values = np.asarray(obs_values, dtype=float)
+    obs_var = (np.mean(obs_values, axis=0) / SNR) ** 2
+    Co = np.array(cov_obs, dtype=float) + np.sum(obs_var) * np.eye(np.asarray(cov_obs).shape[0])
+    return cov - cov_state_obs.dot(np.linalg.solve(Co, cov_state_obs.T))
+
+
 # --------------------------------------------------------------------------------------
 # G3 / G4: locally linear rewrites  (rewrite_odes_as_local_linear_combinations.py)
 # --------------------------------------------------------------------------------------
@@ -272,8 +280,12 @@ def theta_step(X, lin: Linearisation, D, A=None):
 # P4: state sweep  (proxies...py:185-262)
 # --------------------------------------------------------------------------------------
 
-def state_sweep(X, theta_star, lin: Linearisation, D, hidden, A=None, cov_states=()):
+def state_sweep(X, theta_star, lin: Linearisation, D, hidden, A=None, cov_states=(), obs_inv_cov=None, obs_mean=None):
     """One sweep over ``hidden`` (ascending index order, proxies...py:195).
+
+    ``obs_inv_cov`` / ``obs_mean`` (opt-in): the observation term the reference keeps commented out at
+    proxies...py:265-266, ``solve(local_scaling + state_pred_inv_cov, local_mean + state_pred_inv_cov .
+    state_pred_mean[:, u])`` (active in the MATLAB original, proxy_for_ind_states.m:92-93).
 
     * coefficients R, r are evaluated on a snapshot of X taken once (:191);
     * ``D @ X[:, k]`` reads the live array (alias at :185, read at :225);
@@ -306,6 +318,9 @@ def state_sweep(X, theta_star, lin: Linearisation, D, hidden, A=None, cov_states
             Aeff = 2.0 * np.diag(lam)
         else:
             Aeff = Mu + np.diag(lam)
+        if obs_inv_cov is not None:
+            Aeff = Aeff + obs_inv_cov
+            rhs = rhs + np.asarray(obs_inv_cov).dot(np.asarray(obs_mean)[:, u])
         X[:, u] = np.linalg.solve(Aeff, rhs)
         if cov is not None:
             covs[u] = cov

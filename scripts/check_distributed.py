@@ -17,6 +17,12 @@ from variational_gradient_matching_for_dynamical_systems_b200.GP_regression impo
 from variational_gradient_matching_for_dynamical_systems_b200.synthetic import lorenz96_problem  # noqa: E402
 
 
+def _sum_int(v, dev):
+    t = torch.tensor([int(v)], device=dev)
+    dist.all_reduce(t)
+    return t.item()
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -47,7 +53,8 @@ def main():
             et = abs(single.get_theta()[0] - multi.get_theta()[0]) / abs(single.get_theta()[0])
             errs.append((ex, et))
         res[tag] = {"state_rel_err": max(e[0] for e in errs), "theta_rel_err": max(e[1] for e in errs),
-                    "levels": multi.n_levels}
+                    "levels": multi.n_levels, "shift": multi.shift, "cross_rank_live": multi.cross_rank_live,
+                    "tail_overlap_ranks": int(_sum_int(multi.engine.plan.c.n_early > 0, dev))}
     ok = all(v["state_rel_err"] < 1e-10 and v["theta_rel_err"] < 1e-11 for v in res.values())
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -52,12 +52,18 @@ def main():
         timed("allreduce", lambda: dist.all_reduce(e.stats, op=dist.ReduceOp.SUM))
         timed("solve", e.param_solve)
         timed("prepare", e.sweep_prepare)
-        for lev in range(eng.n_levels):
-            if lev > 0:
-                timed("halo%d" % lev, lambda: eng.halo(e.X))
-            timed("level%d" % lev, lambda: e.sweep_level(lev))
+        if not eng.cross_rank_live:
+            timed("levels", e.sweep_levels)
+        else:
+            for lev in range(eng.n_levels):
+                if lev > 0:
+                    timed("halo%d" % lev, lambda: eng.halo(e.X))
+                timed("level%d" % lev, lambda: e.sweep_level(lev))
         timed("barrier", dist.barrier)
     out = {k: round(v / 3, 3) for k, v in phases.items()}
+    out["info"] = dict(e.last_info)
+    out["n_hidden_local"] = e.plan.n_hidden
+    out["tail_overlap"] = int(e.plan.c.n_early)
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

@@ -826,6 +826,78 @@ def test_fitting_state_observations_vs_reference_golden(pkg):
     mean, inv_cov = GP.fitting_state_observations(obs, names, float(g["SNR"]), g["t"], g["C"], g["Cobs"], g["Cso"])
     assert relerr(mean.values, g["mean"]) < TOL
     assert list(mean.columns) == names
+    # state_pred_inv_cov: the predictive covariance it inverts is the well-posed quantity (its singular values span
+    # 4 .. 1e-17, so the pinv of :46 itself depends on which of them fall below the SVD cut-off) ...
+    P_ref = vo.predictive_cov(g["Y"], float(g["SNR"]), g["C"], g["Cobs"], g["Cso"])
+    assert isinstance(inv_cov, GP.LazyPseudoInverse) and inv_cov.shape == g["inv_cov"].shape
+    assert np.max(np.abs(inv_cov.pred_cov - P_ref)) < 1e-12 * np.max(np.abs(g["C"]))
+    # ... and what np.asarray() hands out is a Moore-Penrose inverse of it to the accuracy the reference's own
+    # matrix reaches (P G P = P), computed by the same np.linalg.pinv call
+    G = np.asarray(inv_cov)
+    mp = lambda Gm: np.linalg.norm(P_ref @ Gm @ P_ref - P_ref) / np.linalg.norm(P_ref)
+    assert G.shape == g["inv_cov"].shape and mp(G) < max(10 * mp(g["inv_cov"]), 1e-8)
+    # an observed column that is not among hidden_states gets its own column (the reference's assignment creates it)
+    obs2 = obs.rename(columns={obs.columns[0]: "_extra"})
+    mean2, _ = GP.fitting_state_observations(obs2, names, float(g["SNR"]), g["t"], g["C"], g["Cobs"], g["Cso"])
+    assert list(mean2.columns) == names + ["_extra"]
+    assert relerr(mean2["_extra"].values, g["mean"][:, g["obs_cols"][0]]) < TOL
+    # no observed columns at all: every mean stays zero, the predictive covariance uses the noise-free cov_obs
+    mean0, inv0 = GP.fitting_state_observations(obs.iloc[:, :0], names, float(g["SNR"]), g["t"], g["C"],
+                                                g["Cobs"] + 1e-6 * np.eye(len(g["t2"])), g["Cso"])
+    P0 = g["C"] - g["Cso"] @ np.linalg.solve(g["Cobs"] + 1e-6 * np.eye(len(g["t2"])), g["Cso"].T)
+    assert np.all(mean0.values == 0.0) and np.max(np.abs(inv0.pred_cov - P0)) < 1e-7 * np.max(np.abs(g["C"]))
+
+
+def test_observation_term_opt_in_vs_reference_golden(pkg):
+    """The observation term of the state update (opt-in): the statement the reference keeps commented out at
+    proxies...py:265-266, against the live reference run with exactly that statement activated
+    (oracle/make_golden_obs_term.py) and against the oracle."""
+    p, _lib, engine = pkg
+    g = load("lorenz96_K10_T40_obs_term.npz")
+    K = len(g["names"])
+    names = [str(s) for s in g["names"]]
+    hidden = [u for u in range(K) if names[u] not in [str(s) for s in g["observed"]]]
+    ops = engine.Operators(g["D"], g["A"], obs_inv_cov=g["Q"])
+    eng = engine.VGMEngine(p.OdeModel.lorenz96(K), ops, None, hidden=hidden)
+    eng.set_observation_mean(g["mu"])
+    eng.set_states(g["X0"])
+    for it in range(g["states"].shape[0]):
+        eng.compute_DX()
+        eng.state_sweep()
+        assert relerr(eng.get_states(), g["states"][it]) < TOL, it
+    # without the term the same engine class reproduces the plain golden (nothing leaks between Operators objects)
+    g0 = load("lorenz96_K10_T40.npz")
+    plain = engine.VGMEngine(p.OdeModel.lorenz96(K), g0["D"], g0["A"], hidden=hidden)
+    plain.set_states(g0["X0"])
+    plain.iteration()
+    assert relerr(plain.get_states(), g0["states"][0]) < TOL
+    with pytest.raises(ValueError, match="obs_inv_cov"):
+        plain.set_observation_mean(g["mu"])
+
+
+def test_observation_term_long_grid_vs_oracle(pkg):
+    """Same opt-in on a grid beyond the direct solver (T = 256: shared M + Q is dense, iterative solvers)."""
+    import sympy as sym
+    p, _lib, engine = pkg
+    K, T = 12, 256
+    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=31)
+    rng = np.random.default_rng(32)
+    X0 = Xtrue.copy()
+    X0[:, 1::2] += 0.5 * rng.standard_normal((T, K // 2))
+    D, A, Cm, *_ = vo.kernel_function(t, t[:2], "rbf", [0.0625, 1.0])
+    Q = np.linalg.inv(Cm + 0.5 * np.eye(T))
+    Q = 0.5 * (Q + Q.T)
+    mu = X0 + 0.2 * rng.standard_normal(X0.shape)
+    hidden = list(range(1, K, 2))
+    names = ["_x_%d" % (i + 1) for i in range(K)]
+    lin = vo.Linearisation(vo.parse_ode_lines(vo.lorenz96_ode_lines(K)), sym.symbols(names), sym.symbols(["_alpha"]))
+    Xref, _ = vo.state_sweep(X0, [8.0], lin, D, hidden, obs_inv_cov=Q, obs_mean=mu)
+    eng = engine.VGMEngine(p.OdeModel.lorenz96(K), engine.Operators(D, None, obs_inv_cov=Q), None, hidden=hidden)
+    eng.set_observation_mean(mu)
+    eng.set_states(X0)
+    eng.compute_DX()
+    eng.state_sweep()
+    assert relerr(eng.get_states(), Xref) < TOL, eng.last_info
 
 
 def test_sklearn_compatible_kernels_hit_the_cuda_kernel(pkg):

@@ -200,3 +200,29 @@ def test_sampled_columns_restatement_equals_full_sweep(K, every_second):
     got = vo.lorenz96_sweep_columns(snap, live, K, 8.0, D, cols, hidden)
     for u in cols:
         assert relerr(got[u], full[:, u]) < 1e-12, u
+
+
+def test_observation_term_oracle_matches_the_activated_reference_statement():
+    """oracle.state_sweep(obs_inv_cov=, obs_mean=) against the live reference run with its own commented-out statement
+    (proxies...py:265-266) activated -- golden from oracle/make_golden_obs_term.py."""
+    g = load("lorenz96_K10_T40_obs_term.npz")
+    names = [str(s) for s in g["names"]]
+    K = len(names)
+    hidden = [u for u in range(K) if names[u] not in [str(s) for s in g["observed"]]]
+    lin = vo.Linearisation(vo.parse_ode_lines(vo.lorenz96_ode_lines(K)), sym.symbols(names), sym.symbols(["_alpha"]))
+    X = g["X0"]
+    for it in range(g["states"].shape[0]):
+        X, _ = vo.state_sweep(X, [8.0], lin, g["D"], hidden, obs_inv_cov=g["Q"], obs_mean=g["mu"])
+        assert relerr(X, g["states"][it]) < 1e-11
+    # the term changes the answer (this is not the plain sweep)
+    plain, _ = vo.state_sweep(g["X0"], [8.0], lin, g["D"], hidden)
+    assert relerr(plain, g["states"][0]) > 1e-4
+
+
+def test_predictive_cov_is_what_the_reference_inverts():
+    g = load("fitting_state_observations.npz")
+    P = vo.predictive_cov(g["Y"], float(g["SNR"]), g["C"], g["Cobs"], g["Cso"])
+    G = g["inv_cov"]                                       # the live reference's pinv(P)
+    # P has singular values from 4 down to 1e-17: the pinv is only a Moore-Penrose inverse to ~1e-3 (rounding amplified by
+    # the retained 1/s ~ 1e14), which is why parity on state_pred_inv_cov itself is not well posed
+    assert np.linalg.norm(P @ G @ P - P) / np.linalg.norm(P) < 1e-2

@@ -90,36 +90,82 @@ def kernel_function(time_points, time_points2, kernel_type='RQ', kernel_param=[0
     return c(o["D"], T, T), c(o["A"], T, T), c(o["C"], T, T), c(o["Cobs"], T2, T2), c(o["Cso"], T, T2)
 
 
+class LazyPseudoInverse:
+    """``state_pred_inv_cov`` of ``fitting_state_observations``: the Moore-Penrose inverse of the predictive
+    covariance (GP_regression.py:46), computed on first use.  The analytical updates never read it
+    (proxies_for_ode_parameters_and_states.py:265-266 is commented out), so the default path does not pay for a
+    T x T SVD on the host; ``np.asarray(x)`` (or any indexing / arithmetic through NumPy) materialises it with
+    ``np.linalg.pinv``, exactly what the reference calls.  ``pred_cov`` is the matrix it inverts."""
+
+    def __init__(self, pred_cov):
+        self.pred_cov = np.asarray(pred_cov, dtype=np.float64)
+        self._pinv = None
+
+    shape = property(lambda self: self.pred_cov.shape)
+    dtype = property(lambda self: self.pred_cov.dtype)
+    ndim = 2
+
+    def __array__(self, dtype=None, copy=None):
+        if self._pinv is None:
+            self._pinv = np.linalg.pinv(self.pred_cov)           # GP_regression.py:46
+        return self._pinv if dtype is None else self._pinv.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.__array__()[idx]
+
+    def __len__(self):
+        return self.pred_cov.shape[0]
+
+    def dot(self, other):
+        return self.__array__().dot(other)
+
+    def __matmul__(self, other):
+        return self.__array__() @ other
+
+    def __rmatmul__(self, other):
+        return other @ self.__array__()
+
+
 def fitting_state_observations(observations, hidden_states, SNR, time_points, cov, cov_obs, cov_func_obs,
                                fig_shape=(10, 8)):
     """GP fit of the observed states = initial state proxy (GP_regression.py:33-51).
 
     Reproduces the reference's accumulating-noise behaviour (``cov_obs`` is reassigned inside
     the loop at :42, so observed state i sees sum_{j<=i} sigma_j^2), leaves unobserved states
-    at zero (:38) and returns ``(state_pred_mean DataFrame T x K, state_pred_inv_cov)``.
-    The solves run on the device: SPD inverse by Cholesky (vgm_spd_inverse) + DMMA GEMMs."""
+    at zero (:38), adds a column for an observed state that is not in ``hidden_states`` (as the reference's
+    ``state_pred_mean[state] = ...`` does) and returns ``(state_pred_mean DataFrame T x K, state_pred_inv_cov)``.
+    Everything runs in ``vgm_gp_fit``: Cholesky SOLVES of cov_obs (no explicit inverse) and DMMA GEMMs;
+    ``state_pred_inv_cov`` is a :class:`LazyPseudoInverse` (the SVD-based pinv of :46 only on request)."""
     import pandas as pd
     lib = _lib.load()
     dev = _lib.require_cuda()
-    Y = np.asarray(observations.values, dtype=np.float64)
-    obs_variance = (np.mean(Y, axis=0) / SNR) ** 2
-    T, T2 = len(time_points), Y.shape[0]
+    Y = np.array(observations.values, dtype=np.float64, copy=True)
+    obs_variance = (np.mean(Y, axis=0) / SNR) ** 2 if Y.shape[1] else np.zeros(0)
+    T, T2, n_obs = len(time_points), np.asarray(cov_obs).shape[0], Y.shape[1]
     names = list(map(str, hidden_states))
+    ld, ld2 = _round_up(T, 8), _round_up(T2, 8)
+
+    def padded(M, rows, cols, l):
+        out = torch.zeros((max(rows, 1), l), dtype=torch.float64, device=dev)
+        out[:rows, :cols] = torch.as_tensor(np.array(M, dtype=np.float64, copy=True), device=dev)
+        return out
+    Co, Cso, Cm = padded(cov_obs, T2, T2, ld2), padded(cov_func_obs, T, T2, ld2), padded(cov, T, T, ld)
+    Yd = padded(Y.T, n_obs, T2, ld2)
+    mean_d = torch.zeros((max(n_obs, 1), ld), dtype=torch.float64, device=dev)
+    pc_d = torch.zeros((T, ld), dtype=torch.float64, device=dev)
+    n = lib.vgm_gp_fit_ws_bytes(T, T2, ld2)
+    ws = torch.empty(n + 256, dtype=torch.uint8, device=dev)
+    var = (C.c_double * max(n_obs, 1))(*[float(v) for v in obs_variance])
+    _lib.check(lib.vgm_gp_fit(Co.data_ptr(), Cso.data_ptr(), Cm.data_ptr(), T, T2, ld, ld2, Yd.data_ptr(), var, n_obs,
+                              mean_d.data_ptr(), pc_d.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr()))
+    fit = mean_d[:n_obs, :T].cpu().numpy()
+    cols = list(names)
     mean = np.zeros((T, len(names)))
-    ld2 = _round_up(T2, 8)
-    Co = torch.zeros((T2, ld2), dtype=torch.float64, device=dev)
-    Co[:, :T2] = torch.as_tensor(np.asarray(cov_obs, dtype=np.float64), device=dev)
-    Cso = torch.as_tensor(np.asarray(cov_func_obs, dtype=np.float64), device=dev)
-    n = lib.vgm_gm_operators_ws_bytes(T2, ld2)
-    ws = torch.empty(n, dtype=torch.uint8, device=dev)
-    inv = torch.zeros_like(Co)
-    eye = torch.eye(T2, dtype=torch.float64, device=dev)
     for i, state in enumerate(list(observations.columns)):
-        Co[:, :T2] += obs_variance[i] * eye
-        _lib.check(lib.vgm_spd_inverse(Co.data_ptr(), T2, ld2, inv.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr()))
-        y = torch.as_tensor(Y[:, i], device=dev)
-        mean[:, names.index(str(state))] = (Cso @ (inv[:, :T2] @ y)).cpu().numpy()
-    pred_cov = np.asarray(cov, dtype=np.float64) - (Cso @ (inv[:, :T2] @ Cso.t())).cpu().numpy()
-    state_pred_inv_cov = np.linalg.pinv(pred_cov)      # unused by the analytical path (:46)
-    state_pred_mean = pd.DataFrame(mean, columns=names, index=time_points).rename_axis('time')
-    return state_pred_mean, state_pred_inv_cov
+        key = str(state)
+        if key not in cols:                     # the reference's column assignment creates it
+            cols.append(key)
+            mean = np.concatenate([mean, np.zeros((T, 1))], axis=1)
+        mean[:, cols.index(key)] = fit[i]
+    state_pred_mean = pd.DataFrame(mean, columns=cols, index=time_points).rename_axis('time')
+    return state_pred_mean, LazyPseudoInverse(pc_d[:, :T].cpu().numpy())

@@ -61,7 +61,7 @@ class Operators(C.Structure):
     _fields_ = [("D", c_dp), ("DT", c_dp), ("M", c_dp), ("G", c_dp), ("G_bf16", c_dp), ("M_bf16x2", c_dp),
                 ("G_shift", C.c_double), ("precond_c", C.c_double),
                 ("band_D", C.c_int), ("band_M", C.c_int), ("band_M_lp", C.c_int), ("band_G", C.c_int),
-                ("DtD", c_dp)]
+                ("DtD", c_dp), ("obs_rhs", c_dp)]
 
 
 class SolverOpts(C.Structure):
@@ -90,6 +90,7 @@ _P = C.POINTER
 SIGNATURES = {
     "vgm_last_error": (C.c_char_p, []),
     "vgm_version": (C.c_int, []),
+    "vgm_shutdown": (C.c_int, []),
     "vgm_kernel_build": (C.c_int, [C.c_int, _P(C.c_double), C.c_int, c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int,
                                    c_dp, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "vgm_dgemm_nt": (C.c_int, [_P(GemmArgs), C.c_void_p]),
@@ -108,6 +109,9 @@ SIGNATURES = {
                                    C.c_void_p]),
     "vgm_gm_operators_lu": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, C.c_size_t, C.c_void_p]),
     "vgm_spd_inverse": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_size_t, C.c_void_p]),
+    "vgm_gp_fit_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "vgm_gp_fit": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, _P(C.c_double), C.c_int, c_dp,
+                             c_dp, c_dp, C.c_size_t, C.c_void_p]),
     "vgm_program_builtin": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
     "vgm_program_load": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int, _P(C.c_void_p)]),
     "vgm_program_free": (C.c_int, [C.c_void_p]),

@@ -20,6 +20,20 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_device = -1;
+int device_guard() {
+  int dev = -1;
+  VGM_CUDA_OK(cudaGetDevice(&dev));
+  if (g_device < 0) g_device = dev;
+  if (dev != g_device) {
+    set_error("libvgm_b200 was first used on CUDA device %d and is now called on device %d: one process drives one GPU "
+              "(internal streams, CUDA graphs and kernel attributes are per process)", g_device, dev);
+    return VGM_EINVAL;
+  }
+  return VGM_OK;
+}
+void ir_graph_cache_clear();
+
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s);
 int param_stats_range(const vgm_program* prog, const double* X, const double* DX, int ld, int T, int j0, int j1,
                       const int* ode_class, const int* ode_idx, const int* ode_state, double* partial, cudaStream_t s);
@@ -71,7 +85,14 @@ ProfScope::~ProfScope() {
 using namespace vgm;
 
 extern "C" const char* vgm_last_error(void) { return g_err; }
-extern "C" int vgm_version(void) { return 101; }
+extern "C" int vgm_version(void) { return 102; }
+// Drops the cached CUDA graphs of the correction sequence (they hold raw pointers into workspaces that the caller
+// may since have freed) and forgets the device binding.  Safe to call at any time; everything is rebuilt on demand.
+extern "C" int vgm_shutdown(void) {
+  ir_graph_cache_clear();
+  g_device = -1;
+  return VGM_OK;
+}
 
 extern "C" int vgm_profile_enable(int on) {
   g_prof_on = (on != 0);
@@ -120,6 +141,7 @@ extern "C" int vgm_iteration_device(const vgm_program* prog, const vgm_model_tab
                                     double* theta, double* stats, void* ws, size_t ws_bytes, vgm_sweep_info* info,
                                     vgm_stream_t stream) {
   VGM_REQUIRE(prog && model && plan && ops && X && DX && theta && stats && ws, "null argument");
+  VGM_TRY(device_guard());
   VGM_REQUIRE(ws_bytes >= vgm_iteration_ws_bytes(model, plan), "iteration workspace too small");
   VGM_REQUIRE(((uintptr_t)ws % 256) == 0, "workspace must be 256-byte aligned");
   VGM_REQUIRE(model->n_param == vgm_program_n_param(prog) && model->n_param <= 8, "parameter count");
@@ -327,6 +349,7 @@ extern "C" int vgm_iteration_host(const vgm_program* prog, const vgm_model_table
                                   double* stats_dev, void* ws, size_t ws_bytes, vgm_sweep_info* info,
                                   vgm_stream_t stream) {
   VGM_REQUIRE(model && plan && X_host_in && X_host_out && theta_host && X_dev, "null argument");
+  VGM_TRY(device_guard());
   cudaStream_t s = (cudaStream_t)stream;
   if (model->pipe_chunks >= 2 && plan->n_hidden > 0) {
     VGM_REQUIRE(prog && ops && DX_dev && theta_dev && stats_dev && ws, "null argument");

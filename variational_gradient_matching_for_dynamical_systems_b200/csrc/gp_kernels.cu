@@ -594,6 +594,72 @@ extern "C" int vgm_gm_operators_lu(const double* C, const double* dC, const doub
   return VGM_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// GP_regression.fitting_state_observations, GP_regression.py:33-51: the GP fit of the observed states.
+// ------------------------------------------------------------------------------------
+namespace vgm {
+__global__ void add_to_diagonal_kernel(double* __restrict__ S, int ld, int T, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) S[(size_t)i * ld + i] += v;
+}
+static size_t gp_fit_ws_bytes(int T, int T2, int ld2) {
+  return chol_ws_bytes(T2, ld2) + align_up((size_t)T2 * ld2 * sizeof(double), 256) /*S*/ +
+         align_up((size_t)ld2 * sizeof(double), 256) /*alpha*/ + align_up((size_t)T * ld2 * sizeof(double), 256) /*R*/;
+}
+}  // namespace vgm
+
+extern "C" size_t vgm_gp_fit_ws_bytes(int T, int T2, int ld2) { return gp_fit_ws_bytes(T, T2, ld2); }
+
+extern "C" int vgm_gp_fit(const double* Cobs, const double* Cso, const double* Cmat, int T, int T2, int ld, int ld2,
+                          const double* Y, const double* obs_var_host, int n_obs, double* mean, double* pred_cov,
+                          void* ws, size_t ws_bytes, vgm_stream_t stream) {
+  VGM_REQUIRE(Cobs && Cso && T > 0 && T2 > 0 && ld >= T && ld2 >= T2 && (ld % 2) == 0 && (ld2 % 2) == 0, "gp_fit shapes");
+  VGM_REQUIRE(n_obs >= 0 && (n_obs == 0 || (Y && obs_var_host && mean)), "gp_fit observations");
+  VGM_REQUIRE(!pred_cov || Cmat, "the predictive covariance needs cov");
+  VGM_REQUIRE(ws && ws_bytes >= gp_fit_ws_bytes(T, T2, ld2) && ((uintptr_t)ws % 256) == 0, "gp_fit workspace");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* p = (char*)ws;
+  CholWs w;
+  VGM_TRY(chol_ws_carve(p, chol_ws_bytes(T2, ld2), T2, ld2, w));
+  p += align_up(chol_ws_bytes(T2, ld2), 256);
+  double* S = (double*)p; p += align_up((size_t)T2 * ld2 * sizeof(double), 256);
+  double* alpha = (double*)p; p += align_up((size_t)ld2 * sizeof(double), 256);
+  double* R = (double*)p;
+  VGM_CUDA_OK(cudaMemcpyAsync(S, Cobs, (size_t)T2 * ld2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  bool factored = false;
+  for (int i = 0; i < n_obs; ++i) {
+    // cov_obs is REASSIGNED inside the reference's loop (:42): observed state i sees sum_{j<=i} sigma_j^2
+    add_to_diagonal_kernel<<<ceil_div(T2, 128), 128, 0, s>>>(S, ld2, T2, obs_var_host[i]);
+    VGM_LAUNCH_OK();
+    VGM_TRY(factor_into_ws(S, T2, ld2, w, s));
+    VGM_TRY(check_pivot(w, s));
+    factored = true;
+    // alpha = y_i S^-1 (S symmetric), mean_i = Cso alpha                                            (:43)
+    VGM_CUDA_OK(cudaMemcpyAsync(alpha, Y + (size_t)i * ld2, (size_t)ld2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    VGM_TRY(chol_solve_right(w.L, w.LT, ld2, T2, alpha, ld2, 1, s));
+    vgm_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.A = alpha; g.lda = ld2; g.B = Cso; g.ldb = ld2; g.C = mean + (size_t)i * ld; g.ldc = ld;
+    g.N = 1; g.M = T; g.K = T2; g.alpha = 1.0;
+    VGM_TRY(dgemm_nt(g, s));
+  }
+  if (pred_cov) {
+    // state_pred_cov = cov - Cso solve(cov_obs, Cso^T) with the FINAL accumulated cov_obs            (:45)
+    if (!factored) {
+      VGM_TRY(factor_into_ws(S, T2, ld2, w, s));
+      VGM_TRY(check_pivot(w, s));
+    }
+    VGM_CUDA_OK(cudaMemcpyAsync(R, Cso, (size_t)T * ld2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    VGM_TRY(chol_solve_right(w.L, w.LT, ld2, T2, R, ld2, T, s));
+    vgm_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.A = R; g.lda = ld2; g.B = Cso; g.ldb = ld2; g.C = pred_cov; g.ldc = ld; g.C0 = Cmat;
+    g.N = T; g.M = T; g.K = T2; g.alpha = -1.0; g.beta = 1.0;
+    VGM_TRY(dgemm_nt(g, s));
+  }
+  return VGM_OK;
+}
+
 extern "C" int vgm_spd_inverse(const double* S, int T, int ld, double* Sinv, void* ws, size_t ws_bytes,
                                vgm_stream_t stream) {
   VGM_REQUIRE(S && Sinv && T > 0 && (ld % 2) == 0 && ld >= T, "spd_inverse arguments");

@@ -500,6 +500,11 @@ static IrGraphEntry g_ir_graphs[IR_GRAPH_CACHE];
 static int g_ir_graph_count = 0, g_ir_graph_next = 0;
 static const bool g_no_graph = getenv("VGM_NO_GRAPH") != nullptr;
 constexpr int IR_CHUNK_MIN_ROWS = 4096;   // a chunk is at least this many rows; smaller levels run as one chunk
+void ir_graph_cache_clear() {
+  for (int i = 0; i < g_ir_graph_count; ++i)
+    if (g_ir_graphs[i].exec) { cudaGraphExecDestroy(g_ir_graphs[i].exec); g_ir_graphs[i].exec = nullptr; }
+  g_ir_graph_count = g_ir_graph_next = 0;
+}
 static int ir_chunk_target() {
   static int n = 0;
   if (!n) {
@@ -879,6 +884,7 @@ static int state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* pl
   g.U1 = pl->ruu_const ? nullptr : w.Ruu;
   g.V1 = w.ruu;
   g.g1 = pl->ruu_const ? -pl->ruu_value : -1.0;
+  if (ops->obs_rhs) { g.V2 = ops->obs_rhs; g.g2 = 1.0; }      // + Q mu_u (opt-in observation term)
   g.band = ops->band_D;
   VGM_TRY(dgemm_nt(g, s));
   if (info) { info->gemm_calls += 1; info->kernel_launches += 2; }
@@ -909,6 +915,7 @@ int state_sweep_prepare_range(const vgm_program* prog, const vgm_sweep_plan* pl,
   g.U1 = pl->ruu_const ? nullptr : w.Ruu + o;
   g.V1 = w.ruu + o;
   g.g1 = pl->ruu_const ? -pl->ruu_value : -1.0;
+  if (ops->obs_rhs) { g.V2 = ops->obs_rhs + o; g.g2 = 1.0; }
   g.band = ops->band_D;
   VGM_TRY(dgemm_nt(g, s));
   if (info) { info->gemm_calls += 1; info->kernel_launches += 2; }
@@ -1237,6 +1244,7 @@ extern "C" int vgm_pcg_solve(const vgm_operators* ops, int ruu_const, const doub
                              int n_rows, int T, int ld, const vgm_solver_opts* opts, void* ws, size_t ws_bytes,
                              vgm_sweep_info* info, vgm_stream_t stream) {
   VGM_REQUIRE(Lambda && rhs && X && slot_state && rows && n_rows >= 0 && n_hidden >= n_rows, "null argument");
+  VGM_TRY(device_guard());
   PcgWs w;
   VGM_TRY(pcg_carve(ws, ws_bytes, n_hidden, T, ld, w));
   if (info) memset(info, 0, sizeof(*info));
@@ -1250,17 +1258,20 @@ extern "C" int vgm_pcg_solve(const vgm_operators* ops, int ruu_const, const doub
 extern "C" int vgm_state_sweep_prepare(const vgm_program* prog, const vgm_sweep_plan* plan, const vgm_operators* ops,
                                        const double* X, const double* DX0, const double* theta_star, void* ws,
                                        size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream) {
+  VGM_TRY(device_guard());
   return state_sweep_prepare(prog, plan, ops, X, DX0, theta_star, ws, ws_bytes, info, (cudaStream_t)stream);
 }
 
 extern "C" int vgm_state_sweep_level(const vgm_sweep_plan* plan, const vgm_operators* ops, const vgm_solver_opts* opts,
                                      double* X, int level, void* ws, size_t ws_bytes, vgm_sweep_info* info,
                                      vgm_stream_t stream) {
+  VGM_TRY(device_guard());
   return state_sweep_level(plan, ops, opts, X, level, ws, ws_bytes, info, (cudaStream_t)stream);
 }
 
 extern "C" int vgm_state_sweep_levels(const vgm_sweep_plan* plan, const vgm_operators* ops, const vgm_solver_opts* opts,
                                       double* X, void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream) {
+  VGM_TRY(device_guard());
   return state_sweep_levels(plan, ops, opts, X, ws, ws_bytes, info, (cudaStream_t)stream);
 }
 
@@ -1269,5 +1280,6 @@ extern "C" size_t vgm_state_sweep_ws_bytes(const vgm_sweep_plan* plan) { return 
 extern "C" int vgm_state_sweep(const vgm_program* prog, const vgm_sweep_plan* plan, const vgm_operators* ops,
                                const vgm_solver_opts* opts, double* X, const double* DX0, const double* theta_star,
                                void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream) {
+  VGM_TRY(device_guard());
   return state_sweep(prog, plan, ops, opts, X, DX0, theta_star, ws, ws_bytes, info, (cudaStream_t)stream);
 }

@@ -10,6 +10,10 @@
 namespace vgm {
 
 void set_error(const char* fmt, ...);
+// The library keeps a few process-wide resources (internal streams, events, cached CUDA graphs, kernel attributes)
+// that belong to ONE device: one process drives one GPU.  Returns VGM_EINVAL when the calling thread's current device
+// is not the one the library was first used on.
+int device_guard();
 
 #define VGM_CUDA_OK(expr)                                                              \
   do {                                                                                 \

@@ -352,17 +352,24 @@ class DistributedVGMEngine:
         self.halo(e.X)                                   # neighbours' boundary rows (snapshot)
         e.compute_DX()
         e.param_stats()
-        dist.all_reduce(e.stats, op=dist.ReduceOp.SUM, group=self.group)
-        e.param_solve()
+        # With the reference's literal theta in the state update (proxies...py:211) the sweep does not read the new
+        # theta: the all-reduce then runs beside the sweep and nobody waits for the slowest rank in mid-iteration.
+        late_theta = e.theta_mode == "reference"
+        work = dist.all_reduce(e.stats, op=dist.ReduceOp.SUM, group=self.group, async_op=late_theta)
+        if not late_theta:
+            e.param_solve()
         e.sweep_prepare()
         if not self.cross_rank_live:
             # every live read stays on its rank: the levels run back to back, nobody waits for anybody
             e.sweep_levels(allow_unconverged=allow_unconverged)
-            return e.last_info
-        for lev in range(self.n_levels):
-            if lev > 0:
-                self.halo(e.X)                           # rows updated by their owners in level lev-1
-            e.sweep_level(lev, allow_unconverged=allow_unconverged)
+        else:
+            for lev in range(self.n_levels):
+                if lev > 0:
+                    self.halo(e.X)                       # rows updated by their owners in level lev-1
+                e.sweep_level(lev, allow_unconverged=allow_unconverged)
+        if late_theta:
+            work.wait()
+            e.param_solve()
         return e.last_info
 
     def get_theta(self):

@@ -34,7 +34,9 @@ def _host_i32(a):
 class Operators:
     """D = dC C^-1 (T x T) and friends on the device, padded to leading dimension ld."""
 
-    def __init__(self, D, A=None, ld=None, device=None):
+    def __init__(self, D, A=None, ld=None, device=None, obs_inv_cov=None):
+        """``obs_inv_cov`` (T x T, symmetric positive semi-definite; opt-in) adds the observation term the reference
+        keeps commented out at proxies...py:265-266: every system matrix becomes ``local_scaling + obs_inv_cov``."""
         self.dev = device or _lib.require_cuda()
         D = np.asarray(D, dtype=np.float64) if not torch.is_tensor(D) else D
         T = D.shape[0]
@@ -56,6 +58,7 @@ class Operators:
         self.band_M = self.band_M_lp = self.band_G = 0
         self.band_D = self.band_of(self.D)
         self.DtD = None
+        self.Q = self._pad(obs_inv_cov) if obs_inv_cov is not None else None
 
     # |B[i][j]| <= 2^-64 max|B| beyond the band: dropping it perturbs any product by less than half an
     # ulp of its normwise rounding error, so the banded GEMMs stay FP64-exact in the backward sense.
@@ -88,6 +91,8 @@ class Operators:
             g.N, g.M, g.K = self.T, self.T, self.T
             g.alpha = 1.0
             _lib.check(lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
+            if self.Q is not None:
+                self.DtD += self.Q
         return self.DtD
 
     def ensure_shared_M(self, c):
@@ -95,6 +100,11 @@ class Operators:
         (proxies...py:229,232 with R = c I)."""
         if self.M is not None and self.M_c == c:
             return self.M
+        if self.M is not None:
+            # engines keep raw device pointers to M, G and their bf16 copies: replacing them here would leave an
+            # earlier engine reading freed memory
+            raise ValueError("this Operators object already holds M = (cI - D)^T (cI - D) for c = %r; a model whose "
+                             "constant R_uu is %r needs its own Operators(D, A)" % (self.M_c, c))
         lib = _lib.load()
         T, ld = self.T, self.ld
         BT = -self.DT.clone()                      # (c I - D)^T = c I - D^T, rows K-contiguous
@@ -106,6 +116,8 @@ class Operators:
         g.N = g.M = g.K = T
         g.alpha = 1.0
         _lib.check(lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
+        if self.Q is not None:
+            M += self.Q
         self.M, self.M_c = M, c
         self.band_M = self.band_of(M)
         self.band_M_lp = self.band_of(M, rel=2.0 ** -20)
@@ -323,6 +335,7 @@ class VGMEngine:
         self.theta_star = torch.zeros(max(self.p, 1), dtype=torch.float64, device=self.dev)
         self.stats = torch.zeros(self.p + self.p * self.p, dtype=torch.float64, device=self.dev)
         self._cops = _lib.Operators()
+        self._obs_rhs = None
         self._cops.D, self._cops.DT = self.ops.D.data_ptr(), self.ops.DT.data_ptr()
         self._cops.band_D = self.ops.band_D
         if not self.plan.c.ruu_const and self.T <= Operators.DENSE_MAX_T:
@@ -344,6 +357,39 @@ class VGMEngine:
         self.last_info = None
         self._pipe_cache = {}
         self.last_pipeline = 0
+
+    # ---- opt-in observation term -------------------------------------------------------------
+    def set_observation_mean(self, mu_TK):
+        """Observation term of the state update (opt-in): with ``Operators(obs_inv_cov=Q)`` and ``mu`` (T x K, the GP
+        fit ``state_pred_mean``) state u solves ``(local_scaling + Q) x = local_mean + Q mu_u`` -- the statement the
+        reference keeps commented out (proxies...py:265-266; active in the MATLAB original,
+        archive/VGM_functions/proxy_for_ind_states.m:92-93).  ``None`` switches it off again."""
+        if mu_TK is None:
+            self._obs_rhs = None
+            self._cops.obs_rhs = None
+            return self
+        if self.ops.Q is None:
+            raise ValueError("the observation term needs Operators(..., obs_inv_cov=Q)")
+        if not self.plan.c.ruu_const and self.T > Operators.DENSE_MAX_T:
+            raise NotImplementedError("observation term with a time-varying R_uu needs T <= %d (direct per-CTA solver)"
+                                      % Operators.DENSE_MAX_T)
+        mu = torch.as_tensor(np.asarray(mu_TK, dtype=np.float64), device=self.dev)
+        if mu.shape != (self.T, self.K):
+            raise ValueError("state_pred_mean must be T x K")
+        nh = max(self.plan.n_hidden, 1)
+        rows = torch.zeros((nh, self.ld), dtype=torch.float64, device=self.dev)
+        rows[:self.plan.n_hidden, :self.T] = mu.t()[torch.as_tensor(self.plan.hidden, device=self.dev)]
+        out = torch.zeros_like(rows)
+        g = _lib.GemmArgs()
+        g.A, g.B, g.C = rows.data_ptr(), self.ops.Q.data_ptr(), out.data_ptr()      # Q is symmetric: rows . Q^T
+        g.lda = g.ldb = g.ldc = self.ld
+        g.N, g.M, g.K = self.plan.n_hidden, self.T, self.T
+        g.alpha = 1.0
+        if self.plan.n_hidden:
+            _lib.check(self.lib.vgm_dgemm_nt(C.byref(g), _lib.stream_ptr()))
+        self._obs_rhs = out
+        self._cops.obs_rhs = out.data_ptr()
+        return self
 
     # ---- data movement ---------------------------------------------------------------------
     def set_states(self, X_TK):

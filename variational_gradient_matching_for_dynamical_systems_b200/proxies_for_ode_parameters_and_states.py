@@ -36,15 +36,28 @@ class settings:
     tol = 1e-13                     # relative residual of the per-state solves
     solver = "auto"
     schedule = "reference"          # 'reference' | 'colour' (opt-in parallel multi-colour schedule)
+    observation_term = False        # True: solve(local_scaling + state_pred_inv_cov, local_mean + state_pred_inv_cov
+                                    # . state_pred_mean_u), the statement commented out at proxies...py:265-266
     _warned = False
 
 
-_engines = {}
+_engines = {}          # content key -> VGMEngine (the engine holds the model, so nothing in the key can be recycled)
 
 
 def _fingerprint(M):
-    M = np.asarray(M)
-    return (M.shape, float(M[0, 0]), float(M[-1, -1]), float(M.sum()), float(M[::7, ::13].sum()))
+    """Content hash of an operator: every byte counts (two kernels that agree in a few entries are different)."""
+    import hashlib
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    return (M.shape, hashlib.blake2b(M.tobytes(), digest_size=16).hexdigest())
+
+
+def _model_key(model):
+    """The model by CONTENT: its text, symbols and replication (id() is recycled after garbage collection)."""
+    return (tuple(model.lines), tuple(model.state_names), tuple(model.param_names), model.zero_fill, model.n_copies)
+
+
+def _couplings_key(couplings):
+    return None if couplings is None else tuple(tuple(int(k) for k in lst) for lst in couplings)
 
 
 def _model_of(locally_linear_odes):
@@ -57,20 +70,31 @@ def _model_of(locally_linear_odes):
                     "rewrite_odes_as_linear_combination_in_parameters / _in_states")
 
 
-def _engine(model, D, A, hidden, couplings, theta_mode):
-    key = (id(model), _fingerprint(D), tuple(hidden), None if couplings is None else id(couplings), theta_mode,
-           settings.tol, settings.solver, settings.schedule)
+def _engine(model, D, A, hidden, couplings, theta_mode, obs_inv_cov=None):
+    key = (_model_key(model), _fingerprint(D), tuple(hidden), _couplings_key(couplings), theta_mode,
+           float(settings.theta_literal), settings.tol, settings.solver, settings.schedule,
+           None if obs_inv_cov is None else _fingerprint(obs_inv_cov))
     eng = _engines.get(key)
     if eng is None:
-        if len(_engines) > 8:
-            _engines.clear()
-        ops = Operators(D, A)
+        while len(_engines) >= 8:
+            _engines.pop(next(iter(_engines)))                 # oldest first; the others stay valid (content keys)
+        ops = Operators(D, A, obs_inv_cov=obs_inv_cov)
         literal = tuple([float(settings.theta_literal)] * model.p)
         eng = VGMEngine(model, ops, None, hidden=hidden, couplings=couplings, theta_mode=theta_mode,
                         theta_literal=literal, tol=settings.tol, solver=settings.solver,
                         schedule=settings.schedule)
         _engines[key] = eng
     return eng
+
+
+def _engine_for_parameters(model, D):
+    """Any cached engine of this model and operator serves the theta update (it only needs X, D.X and the
+    statistics kernels); otherwise one without hidden states is built."""
+    mk, fp = _model_key(model), _fingerprint(D)
+    for k, e in _engines.items():
+        if k[0] == mk and k[1] == fp:
+            return e
+    return _engine(model, D, None, (), None, "proxy")
 
 
 def proxy_for_ode_parameters(state_proxy, locally_linear_odes, dC_times_inv_C, eps_cov, ode_param_symbols,
@@ -86,10 +110,7 @@ def proxy_for_ode_parameters(state_proxy, locally_linear_odes, dC_times_inv_C, e
         raise NotImplementedError("optimizer=%r: only the closed-form 'analytical' update runs on the B200 path "
                                   "(the SciPy 'minimizer' branch, proxies...py:114-128, is out of scope)" % (optimizer,))
     model = _model_of(locally_linear_odes)
-    fp = _fingerprint(dC_times_inv_C)
-    eng = next((e for k, e in _engines.items() if k[0] == id(model) and k[1] == fp), None)   # reuse the sweep engine
-    if eng is None:
-        eng = _engine(model, dC_times_inv_C, None, (), None, "proxy")
+    eng = _engine_for_parameters(model, dC_times_inv_C)          # reuses the sweep engine when there is one
     eng.set_states(np.asarray(state_proxy.values, dtype=np.float64))
     eng.compute_DX()
     stats = eng.param_stats().cpu().numpy()
@@ -155,7 +176,9 @@ def proxy_for_ind_states(state_proxy, ode_param_proxy, odes, odes_gradient_state
         theta_mode = "proxy"
     own = getattr(state_couplings, "_ptr", None) is not None
     couplings = None if own else state_couplings
-    eng = _engine(model, dC_times_inv_C, None, tuple(hidden), couplings, theta_mode)
+    Q = np.asarray(state_pred_inv_cov, dtype=np.float64) if settings.observation_term else None
+    eng = _engine(model, dC_times_inv_C, None, tuple(hidden), couplings, theta_mode, obs_inv_cov=Q)
+    eng.set_observation_mean(np.asarray(state_pred_mean.values, dtype=np.float64) if settings.observation_term else None)
     eng.set_states(X)
     eng.compute_DX()
     eng.state_sweep(theta_star=None if theta_mode == "reference" else theta)
