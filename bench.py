@@ -61,6 +61,7 @@ def parse():
                          "of the ranges as fractions; a short first range starts the compute early, a short last "
                          "one shortens the final copy-out; 0 = no pipelining")
     ap.add_argument("--no-profile", action="store_true", help="skip the second, per-kernel-instrumented timed region")
+    ap.add_argument("--no-colour", action="store_true", help="skip the opt-in multi-colour schedule block (N=1 only)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 trajectory-batch block")
     ap.add_argument("--c4-trajectories", type=int, default=65536)
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of sampled hidden columns + theta")
@@ -101,6 +102,21 @@ def cpu_port_run(K_sample, T, steps, warmup):
     return value, total, blas
 
 
+def live_reference_record():
+    """The LIVE reference timed in the build container (scripts/time_live_reference.py -> profiles/
+    cpu_live_reference.json): it cannot travel to the GPU box, so its numbers are quoted, labelled, next to the port
+    that is timed here."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "cpu_live_reference.json")) as f:
+            d = json.load(f)
+        return {"source": "profiles/cpu_live_reference.json (scripts/time_live_reference.py, build container)",
+                "cores": d["cores"], "rows": [{k: r[k] for k in ("K", "hidden", "ms_per_hidden_state",
+                                                                   "state_time_updates_per_s")} for r in d["rows"]],
+                "mean_ms_per_hidden_state": d["mean_ms_per_hidden_state"], "extrapolated": d["extrapolated"]}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -118,7 +134,10 @@ def reference_arm(args):
             "config": {"workload": "Lorenz96 K=%d T=%d, bounded CPU sample K=%d" % (args.K, args.T, Ks),
                        "kernel": KERNEL, "dt": DT},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "blas": blas},
+                             "blas": blas, "live_reference": live_reference_record(),
+                             "note": "this arm times the ORACLE PORT of the reference's algorithm (one dense LAPACK solve "
+                                     "per hidden state, without the reference's 12 dense T^3 GEMMs per state), not the "
+                                     "reference itself, on a bounded sample of the workload"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -198,6 +217,62 @@ def parity_block(args, eng, core, X0_local, world, rank, K, T, hidden, n_columns
     if world > 1:
         flag = torch.tensor([1 if (out is None or out["ok"]) else 0], device=core.X.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Opt-in multi-colour schedule (schedule='colour'): NOT the reference's update order, so no 1e-9 parity is claimed for
+# it.  Its stated tolerance is on the converged hidden-state RMSE against the ground-truth trajectory: within 5 % of
+# the RMSE the reference order reaches after the same number of iterations.
+# ----------------------------------------------------------------------------------------------
+COLOUR_RMSE_TOL = 0.05
+
+
+def colour_block(args, model, ops, hidden, ref_engine, X0_local, K, T, dev, n_conv=8):
+    import torch
+    from variational_gradient_matching_for_dynamical_systems_b200.engine import VGMEngine
+    from variational_gradient_matching_for_dynamical_systems_b200.synthetic import lorenz96_trajectory
+    t0 = time.perf_counter()
+    col = VGMEngine(model, ops, None, hidden=hidden, schedule="colour", solver=args.solver, inner_iters=args.inner_iters,
+                    tol=args.tol, optimistic_passes=args.optimistic_passes)
+    _, Xtrue = lorenz96_trajectory(K, T, DT, seed=0, device=dev)          # the trajectory lorenz96_problem perturbs
+    hid = torch.as_tensor(np.asarray(hidden, dtype=np.int64), device=dev)
+    truth = Xtrue.index_select(0, hid)[:, :T]
+    del Xtrue
+    rmse = lambda X: float(((X.index_select(0, hid)[:, :T] - truth) ** 2).mean().sqrt().item())
+
+    def step():
+        col.X.copy_(X0_local)
+        return col.iteration()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_it = max(3, args.steps)
+    e0.record()
+    for _ in range(n_it):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_it
+    # converged RMSE of both schedules from the same initial proxies
+    r0 = rmse(X0_local)
+    col.X.copy_(X0_local)
+    ref_engine.X.copy_(X0_local)
+    for _ in range(n_conv):
+        col.iteration()
+        ref_engine.iteration()
+    r_col, r_ref = rmse(col.X), rmse(ref_engine.X)
+    ref_engine.X.copy_(X0_local)
+    out = {"schedule": "colour (opt-in; hidden states that read each other's D.x never share a colour)",
+           "levels": int(col.plan.host.n_levels), "level_sizes": np.diff(col.plan.host.level_ptr).tolist(),
+           "ms_per_step": ms, "state_time_updates_per_s": len(hidden) * T / (ms * 1e-3),
+           "iterations_to_converge": n_conv, "rmse_initial": r0, "rmse_colour": r_col, "rmse_reference_order": r_ref,
+           "rmse_vs_reference_order": abs(r_col - r_ref) / r_ref, "tol": COLOUR_RMSE_TOL,
+           "ok": bool(r_col < r0 and abs(r_col - r_ref) <= COLOUR_RMSE_TOL * r_ref + 1e-3),
+           "seconds": round(time.perf_counter() - t0, 2)}
+    del col
+    torch.cuda.empty_cache()
     return out
 
 
@@ -516,6 +591,11 @@ def native_arm(args):
     if not args.no_parity:
         parity = parity_block(args, eng, core, X0_local, world, rank, K, T, hidden, args.parity_columns)
 
+    # ---- opt-in multi-colour schedule, reported separately with its own tolerance (north_star) ---------------
+    colour = None
+    if world == 1 and not args.no_colour:
+        colour = colour_block(args, model, ops, hidden, core, X0_local, K, T, dev)
+
     # ---- config C4 under the same launch (trajectory batch + all-reduce of the pooled statistics) ------------
     c4 = None
     if not args.no_c4:
@@ -582,7 +662,8 @@ def native_arm(args):
         v, total, blas = cpu_port_run(args.cpu_sample_K, T, 1, 0)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": "Lorenz96 K=%d (%d hidden), T=%d, 1 iteration of the oracle port (%.1f s)" %
-                         (args.cpu_sample_K, args.cpu_sample_K // 2, T, total), "blas": blas}
+                         (args.cpu_sample_K, args.cpu_sample_K // 2, T, total), "blas": blas,
+               "live_reference": live_reference_record()}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -601,7 +682,7 @@ def native_arm(args):
                        "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
                              (n_hidden_local * core.ld * 8 / 1e6),
                        "profiled_ms_per_step": (ms_prof / args.steps) if ms_prof else None},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "c4": c4, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "c4": c4, "colour_schedule": colour, "gpu_launches": launches,
             "clocks": clocks,
             "solver_iterations": pcg_iters, "theta": theta, "setup_s": setup_s,
             "evolving_loop": evolving,

@@ -389,6 +389,15 @@ int vgm_iteration_host(const vgm_program* prog, const vgm_model_tables* model, c
                        double* X_host_out, double* theta_host, double* X_dev, double* DX_dev, double* theta_dev, double* stats_dev,
                        void* ws, size_t ws_bytes, vgm_sweep_info* info, vgm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Synthetic Lorenz96 trajectories on the device (data generation; replaces setup_simulation's odeint,
+ * simulate_state_dynamics.py:79-92, for benchmarks -- not a parity target, LSODA is third-party).
+ * Classical RK4 with step h on the ring f_k = (x_{k+1} - x_{k-2}) x_{k-1} - x_k + alpha (Lorenz96_ODEs.txt:1-10):
+ * x0 [K] is the initial state, n_spinup steps are discarded, then X[k][i] = x_k(i * n_sub * h) for i < n_grid
+ * (state-major, leading dimension ld).  n_sub <= 8; scratch holds 2 K doubles.  One launch per grid interval. */
+int vgm_lorenz96_rk4(const double* x0, int K, double alpha, double h, int n_sub, int n_spinup, int n_grid, double* X,
+                     int ld, double* scratch, vgm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

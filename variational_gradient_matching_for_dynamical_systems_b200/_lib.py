@@ -112,6 +112,8 @@ SIGNATURES = {
     "vgm_gp_fit_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vgm_gp_fit": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, _P(C.c_double), C.c_int, c_dp,
                              c_dp, c_dp, C.c_size_t, C.c_void_p]),
+    "vgm_lorenz96_rk4": (C.c_int, [c_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, C.c_int,
+                                   c_dp, C.c_void_p]),
     "vgm_program_builtin": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
     "vgm_program_load": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int, _P(C.c_void_p)]),
     "vgm_program_free": (C.c_int, [C.c_void_p]),

@@ -20,6 +20,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("VGM_NO_PDL") == nullptr;
+  return on;
+}
+
 static int g_device = -1;
 int device_guard() {
   int dev = -1;

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
   double* As = smem;                        // [STAGES][BM][LDS]
   double* Bs = smem + STAGES * BM * LDS;    // [STAGES][BN][LDS]
 
+  pdl_wait();       // launched with programmatic stream serialization (vgm_common.cuh): the predecessor is done from here on
   const int N = a.n_rows_dev ? min(*a.n_rows_dev, a.N) : a.N;
   const int n0 = blockIdx.y * BM;
   if (n0 >= N) return;
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
       }
     }
   }
+  pdl_trigger();    // late: the successor's CTAs are only parked for the moment the last tiles drain
 }
 
 template <class Cfg>
@@ -221,8 +223,7 @@ static int launch_gemm(const vgm_gemm_args& a, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(ceil_div(a.M, Cfg::BN), ceil_div(a.N, Cfg::BM));
-  dgemm_nt_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a);
-  VGM_LAUNCH_OK();
+  VGM_CUDA_OK(launch_pdl(dgemm_nt_kernel<Cfg>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, a));
   return VGM_OK;
 }
 

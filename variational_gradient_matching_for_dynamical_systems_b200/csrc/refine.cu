@@ -6,6 +6,7 @@
 // per step are tcgen05 GEMMs (tc_gemm.cu) writing raw FP32 accumulators; everything elementwise and every
 // dot product of a CG step lives in the two kernels ir_update / ir_dir below.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "vgm_common.cuh"
 #include "vgm_profile.cuh"
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(IR_THREADS)
 ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __restrict__ Lambda,
                      const double* __restrict__ rr, const int* __restrict__ act, const int* __restrict__ n_dev, int T,
                      int ld, double shift, double c) {
+  pdl_wait();
   const int j = blockIdx.x;
   if (n_dev && j >= *n_dev) return;
   const int slot = act[j];
@@ -113,6 +115,7 @@ ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __rest
     st_bf4(b.rsb + oj + i, make_float4(sv.x * r.x, sv.y * r.y, sv.z * r.z, sv.w * r.w));
   }
   if (threadIdx.x == 0) b.sigma[j] = sig;
+  pdl_trigger();
 }
 
 // REG: the row fits one pass (T <= 4 * IR_THREADS), so z / (p, q) stay in registers and the kernel needs no
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, const int* 
                                                             int first) {
   extern __shared__ float ir_sm[];       // z of this row (!REG)
   __shared__ double red[40];
+  pdl_wait();
   const int j = blockIdx.x;
   if (n_dev && j >= *n_dev) return;
   const size_t o = (size_t)j * ld;
@@ -154,6 +158,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_kernel(IrBuf b, const int* 
     st_bf4(b.q_lo + o + i, make_float4(p.x - hi.x, p.y - hi.y, p.z - hi.z, p.w - hi.w));
   }
   if (threadIdx.x == 0) b.rz[j] = rz_new;
+  pdl_trigger();
 }
 
 // One WARP per system (T <= 1024, T % 8 == 0): a lane keeps its 4 groups of 8 elements in registers, every load of
@@ -195,6 +200,7 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) {
 
 __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const int* __restrict__ n_dev, int n, int T,
                                                                  int ld, int first) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * (IR_THREADS / 32) + (threadIdx.x >> 5);
   const int nn = n_dev ? min(*n_dev, n) : n;
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const 
     }
   }
   if (lane == 0) b.rz[j] = rz_new;
+  pdl_trigger();
 }
 
 template <bool REG>
@@ -241,6 +248,7 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
   __shared__ double red[40];
   float* sp = ir_sm;
   float* sq = ir_sm + ((T + 3) & ~3);
+  pdl_wait();
   const int j = blockIdx.x;
   if (n_dev && j >= *n_dev) return;
   const size_t o = (size_t)j * ld;
@@ -287,11 +295,13 @@ __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const in
       st_bf4(b.rsb + o + i, make_float4(sv.x * r.x, sv.y * r.y, sv.z * r.z, sv.w * r.w));
     }
   }
+  pdl_trigger();
 }
 
 __global__ void __launch_bounds__(IR_THREADS)
 ir_finish_kernel(IrBuf b, double* __restrict__ P, double* __restrict__ X, const int* __restrict__ slot_state,
                  const int* __restrict__ act, const int* __restrict__ n_dev, int T, int ld) {
+  pdl_wait();
   const int j = blockIdx.x;
   if (n_dev && j >= *n_dev) return;
   const int slot = act[j];
@@ -304,14 +314,14 @@ ir_finish_kernel(IrBuf b, double* __restrict__ P, double* __restrict__ X, const 
     p[t] = v;
     x[t] = v;
   }
+  pdl_trigger();
 }
 
 int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
                   const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * 16.0, s);   // R in, r32 + rsb out, s16 in (the common case: list unchanged)
-  ir_inner_init_kernel<<<n, IR_THREADS, 0, s>>>(b, R, Lambda, rr, act, n_dev, T, ld, shift, c);
-  VGM_LAUNCH_OK();
+  VGM_CUDA_OK(launch_pdl(ir_inner_init_kernel, dim3(n), dim3(IR_THREADS), 0, s, b, R, Lambda, rr, act, n_dev, T, ld, shift, c));
   return VGM_OK;
 }
 
@@ -319,10 +329,16 @@ int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cu
   if (n <= 0) return VGM_OK;
   // reads acc32 4, s16 2, rsb 2, (p_hi, p_lo 4); writes p_hi, p_lo 4
   ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * (first ? 12.0 : 16.0), s);
-  if (T <= 8 * 32 * IR_WG && (T % 8) == 0) ir_dir_warp_kernel<<<ceil_div(n, IR_THREADS / 32), IR_THREADS, 0, s>>>(b, n_dev, n, T, ld, first);
-  else if (T <= 4 * IR_THREADS) ir_dir_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, first);
-  else ir_dir_kernel<false><<<n, IR_THREADS, ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, first);
-  VGM_LAUNCH_OK();
+  // VGM_IR_DIR_VARIANT=1: one CTA per row with the row in registers (like ir_update) instead of one warp per row
+  static const int variant = getenv("VGM_IR_DIR_VARIANT") ? atoi(getenv("VGM_IR_DIR_VARIANT")) : 0;
+  if (variant == 1 && T <= 4 * IR_THREADS)
+    VGM_CUDA_OK(launch_pdl(ir_dir_kernel<true>, dim3(n), dim3(IR_THREADS), 0, s, b, n_dev, T, ld, first));
+  else if (T <= 8 * 32 * IR_WG && (T % 8) == 0)
+    VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel, dim3(ceil_div(n, IR_THREADS / 32)), dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
+  else if (T <= 4 * IR_THREADS)
+    VGM_CUDA_OK(launch_pdl(ir_dir_kernel<true>, dim3(n), dim3(IR_THREADS), 0, s, b, n_dev, T, ld, first));
+  else
+    VGM_CUDA_OK(launch_pdl(ir_dir_kernel<false>, dim3(n), dim3(IR_THREADS), ((T + 3) & ~3) * sizeof(float), s, b, n_dev, T, ld, first));
   return VGM_OK;
 }
 
@@ -332,9 +348,11 @@ int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, 
   // reads p_hi, p_lo 4, acc32 4, lam32 4, d32 4, (r32 4); writes d32 4, (r32 4, rsb 2)
   ProfScope prof(PROF_IR_UPDATE, 0.0, (double)n * T * ((last ? 20.0 : 30.0) - (first ? 4.0 : 0.0)), s);
   const float sc_num = (float)(shift + c), sc_c = (float)c;
-  if (T <= 4 * IR_THREADS) ir_update_kernel<true><<<n, IR_THREADS, 0, s>>>(b, n_dev, T, ld, last, first, sc_num, sc_c);
-  else ir_update_kernel<false><<<n, IR_THREADS, 2 * ((T + 3) & ~3) * sizeof(float), s>>>(b, n_dev, T, ld, last, first, sc_num, sc_c);
-  VGM_LAUNCH_OK();
+  if (T <= 4 * IR_THREADS)
+    VGM_CUDA_OK(launch_pdl(ir_update_kernel<true>, dim3(n), dim3(IR_THREADS), 0, s, b, n_dev, T, ld, last, first, sc_num, sc_c));
+  else
+    VGM_CUDA_OK(launch_pdl(ir_update_kernel<false>, dim3(n), dim3(IR_THREADS), 2 * ((T + 3) & ~3) * sizeof(float), s, b, n_dev, T, ld,
+                           last, first, sc_num, sc_c));
   return VGM_OK;
 }
 
@@ -342,8 +360,7 @@ int ir_finish(const IrBuf& b, double* P, double* X, const int* slot_state, const
               int T, int ld, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   ProfScope prof(PROF_VEC, 0.0, (double)n * T * 28.0, s);
-  ir_finish_kernel<<<n, IR_THREADS, 0, s>>>(b, P, X, slot_state, act, n_dev, T, ld);
-  VGM_LAUNCH_OK();
+  VGM_CUDA_OK(launch_pdl(ir_finish_kernel, dim3(n), dim3(IR_THREADS), 0, s, b, P, X, slot_state, act, n_dev, T, ld));
   return VGM_OK;
 }
 

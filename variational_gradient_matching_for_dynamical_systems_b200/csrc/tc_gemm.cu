@@ -159,15 +159,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
-  const int row_tiles = (n_rows + TC_BM - 1) / TC_BM;
   const int col_tiles = (a.M + TC_BN - 1) / TC_BN;
-  const int n_tiles = row_tiles * col_tiles;
-  // work items of this CTA: u = u_first, u_first + u_step, ... < u_end;  streaming: u = tile index (row-tile major);
-  // BRES: the column tile is fixed (blockIdx.x % col_tiles) and u runs over the row tiles
-  const int u_first = BRES ? (int)blockIdx.x / col_tiles : (int)blockIdx.x;
-  const int u_step = BRES ? (int)gridDim.x / col_tiles : (int)gridDim.x;
-  const int u_end = BRES ? row_tiles : n_tiles;
   const int ct_fixed = (int)blockIdx.x % col_tiles;
 
   if (threadIdx.x == 0) {
@@ -191,21 +183,35 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  // BRES: the operator tiles of this CTA's column tile are loaded once.  They are constant (M, G), so the load is
+  // issued BEFORE pdl_wait(): it overlaps the tail of the preceding kernel (programmatic dependent launch).
+  if (BRES && warp == 0 && lane == 0) {
+    int kb_lo, kb_hi;
+    tc_k_range(ct_fixed, a.K, a.band, kb_lo, kb_hi);
+    mbar_expect_tx(b_full, (uint32_t)(kb_hi - kb_lo) * PARTS * TC_TILE_BYTES);
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      unsigned char* rb = b_res + (kb - kb_lo) * PARTS * TC_TILE_BYTES;
+      tma_load_2d(rb, &maps.b0, b_full, kb * TC_BK, ct_fixed * TC_BN);
+      if (SPLIT) tma_load_2d(rb + TC_TILE_BYTES, &maps.b1, b_full, kb * TC_BK, ct_fixed * TC_BN);
+    }
+  }
+  pdl_wait();        // everything below reads what earlier kernels wrote (row count, A operand) or writes `out`
+  const int n_rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
+  const int row_tiles = (n_rows + TC_BM - 1) / TC_BM;
+  const int n_tiles = row_tiles * col_tiles;
+  // work items of this CTA: u = u_first, u_first + u_step, ... < u_end;  streaming: u = tile index (row-tile major);
+  // BRES: the column tile is fixed (blockIdx.x % col_tiles) and u runs over the row tiles
+  const int u_first = BRES ? (int)blockIdx.x / col_tiles : (int)blockIdx.x;
+  const int u_step = BRES ? (int)gridDim.x / col_tiles : (int)gridDim.x;
+  const int u_end = BRES ? row_tiles : n_tiles;
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (BRES && u_first < u_end) {                         // the operator tiles of this CTA's column tile, once
-        int kb_lo, kb_hi;
-        tc_k_range(ct_fixed, a.K, a.band, kb_lo, kb_hi);
-        mbar_expect_tx(b_full, (uint32_t)(kb_hi - kb_lo) * PARTS * TC_TILE_BYTES);
-        for (int kb = kb_lo; kb < kb_hi; ++kb) {
-          unsigned char* rb = b_res + (kb - kb_lo) * PARTS * TC_TILE_BYTES;
-          tma_load_2d(rb, &maps.b0, b_full, kb * TC_BK, ct_fixed * TC_BN);
-          if (SPLIT) tma_load_2d(rb + TC_TILE_BYTES, &maps.b1, b_full, kb * TC_BK, ct_fixed * TC_BN);
-        }
-      }
+      // a CTA without work still owns the operator tiles in flight: they must land before its shared memory goes away
+      if (BRES && !(u_first < u_end)) mbar_wait(b_full, 0);
       for (int u = u_first; u < u_end; u += u_step) {
         const int rt = BRES ? u : u / col_tiles, ct = BRES ? ct_fixed : u % col_tiles;
         int kb_lo, kb_hi;
@@ -316,6 +322,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
   if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // output stores done
   tc_fence_before();
   __syncthreads();
+  pdl_trigger();     // late: a successor parked beside a long persistent kernel only costs it issue slots
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
@@ -329,8 +336,42 @@ typedef CUresult (*cuTensorMapEncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, 
                                              CUtensorMapFloatOOBfill);
 static cuTensorMapEncodeTiled_t g_encode = nullptr;
 
+// cuTensorMapEncodeTiled costs ~1 us of host time and a GEMM needs up to five maps; the solver launches the same few
+// (pointer, shape) combinations hundreds of times per sweep, so encoded maps are kept in a small direct-mapped cache.
+struct MapKey {
+  const void* base;
+  int dtype, rows, cols, ld, box_cols, box_rows;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && dtype == o.dtype && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+           box_rows == o.box_rows;
+  }
+};
+constexpr int MAP_CACHE = 64;
+static MapKey g_map_keys[MAP_CACHE];
+static CUtensorMap g_map_vals[MAP_CACHE];
+static bool g_map_used[MAP_CACHE];
+
+static int make_map_uncached(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rows,
+                             int cols, int ld, int box_cols, int box_rows);
+
 static int make_map(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rows, int cols,
                     int ld, int box_cols, int box_rows) {
+  const MapKey key{base, (int)dtype, rows, cols, ld, box_cols, box_rows};
+  size_t h = (size_t)((uintptr_t)base >> 8) * 1000003u + (size_t)rows * 7919u + (size_t)cols * 31u + (size_t)box_rows;
+  const int slot = (int)(h % MAP_CACHE);
+  if (g_map_used[slot] && g_map_keys[slot] == key) {
+    *map = g_map_vals[slot];
+    return VGM_OK;
+  }
+  VGM_TRY(make_map_uncached(map, dtype, elem_bytes, base, rows, cols, ld, box_cols, box_rows));
+  g_map_keys[slot] = key;
+  g_map_vals[slot] = *map;
+  g_map_used[slot] = true;
+  return VGM_OK;
+}
+
+static int make_map_uncached(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rows,
+                             int cols, int ld, int box_cols, int box_rows) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -374,8 +415,7 @@ static int tc_launch(const TcMaps& maps, const TcGemmArgs& args, int n_sm, cudaS
   } else {
     grid = min(row_tiles * col_tiles, n_sm);
   }
-  tc_gemm_kernel<SPLIT, BRES><<<grid, TC_THREADS, Cfg::SMEM, s>>>(maps, args);
-  VGM_LAUNCH_OK();
+  VGM_CUDA_OK(launch_pdl(tc_gemm_kernel<SPLIT, BRES>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, maps, args));
   return VGM_OK;
 }
 
