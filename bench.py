@@ -626,10 +626,19 @@ def native_arm(args):
              "tcgemm": "vgm::tc_gemm_kernel<split|single> (tcgen05 bf16, banded, operator-resident)",
              "ir_update": "vgm::ir_update_kernel", "ir_dir": "vgm::ir_dir_warp_kernel",
              "vec_other": "vgm::ir_inner_init/ir_finish/ir_prep/cg_gather_x", "assemble": "state_assemble + param_stats"}
-    # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/ncu_traffic.json), same shapes
+    # DRAM bytes per launch: NOT measured in this run -- read from the committed `ncu --set full` capture of the same
+    # kernels at the same shape (profiles/r02_ncu_traffic.json, made by scripts/ncu_summarise.py from
+    # scripts/ncu_targets.py at K=100000, T=1000; table in profiles/r02_ncu_summary.md)
+    fam_kernel = {"dgemm": "void dgemm_nt_kernel", "tcgemm": "void tc_gemm_kernel", "ir_update": "void ir_update_kernel",
+                  "ir_dir": "ir_dir_warp_kernel", "assemble": "vgm_lorenz96_state_assemble", "vec_other": "ir_inner_init_kernel"}
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            ncu_traffic = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+            cap = json.load(f)
+        ncu_traffic = {fam_: {"dram_bytes_per_launch": cap[k_]["dram_bytes_per_launch"],
+                              "note": "from committed capture profiles/%s (kernel %s, %.1f us under ncu), see "
+                                      "profiles/r02_ncu_summary.md; not measured in this run" %
+                                      (cap[k_]["capture"], cap[k_]["kernel"], cap[k_]["duration_us"])}
+                       for fam_, k_ in fam_kernel.items() if k_ in cap}
     except Exception:  # noqa: BLE001
         ncu_traffic = {}
     kernels = {}

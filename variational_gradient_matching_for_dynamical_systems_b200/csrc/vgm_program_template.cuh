@@ -18,7 +18,6 @@
 #define VGM_NSTAT (VGM_NPARAM + VGM_NPARAM * (VGM_NPARAM + 1) / 2)
 #define VGM_STAT_ROWS 8      // ODE rows per CTA in the statistics kernel
 #define VGM_PROG_THREADS 256   // max threads per CTA (launch may use fewer, multiple of 32, >= 64)
-#define VGM_ASM_T 4            // time points per thread and pass in the state-assemble kernel
 
 __device__ __forceinline__ double vgm_prog_warp_sum(double v) {
 #pragma unroll
@@ -121,54 +120,34 @@ VGM_PROG(state_assemble)(const double* __restrict__ X, const double* __restrict_
 #pragma unroll
   for (int q = 0; q < VGM_NPARAM; ++q) th[q] = theta[q];
   const int e0 = pair_ptr[i], e1 = pair_ptr[i + 1];
-  // pairs outside, VGM_ASM_T time points per thread inside: the index tables are read once per pair and the
-  // VGM_ASM_T x VGM_ARITY state loads of a pair are independent (per time point the pairs are still summed in c(u)
-  // order, so the result is bit-identical to the straightforward loop)
-  for (int t0 = 0; t0 < T; t0 += VGM_ASM_T * blockDim.x) {
-    double lam[VGM_ASM_T], acc[VGM_ASM_T], r_self[VGM_ASM_T], R_self[VGM_ASM_T];
-#pragma unroll
-    for (int u = 0; u < VGM_ASM_T; ++u) lam[u] = acc[u] = r_self[u] = R_self[u] = 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    double lam = 0.0, acc = 0.0, r_self = 0.0, R_self = 0.0;
     for (int e = e0; e < e1; ++e) {
-      const int j = pair_ode[e], code = pair_code[e], self = pair_self[e], q = pair_live[e];
-      const double* xr[VGM_ARITY];
+      const int j = pair_ode[e];
+      double s[VGM_ARITY];
 #pragma unroll
-      for (int a = 0; a < VGM_ARITY; ++a) xr[a] = X + (size_t)ode_idx[(size_t)j * VGM_ARITY + a] * ld;
-      const double* dxr = DX0 + (size_t)ode_state[j] * ld;
-#pragma unroll
-      for (int u = 0; u < VGM_ASM_T; ++u) {
-        const int t = t0 + threadIdx.x + u * blockDim.x;
-        if (t < T) {
-          double s[VGM_ARITY];
-#pragma unroll
-          for (int a = 0; a < VGM_ARITY; ++a) s[a] = xr[a][t];
-          double R, r;
-          vgm_state_coeffs(code, th, s, R, r);
-          if (self) {
-            R_self[u] = R;
-            r_self[u] = r;
-          } else {
-            if (q < 0) {
-              acc[u] -= R * (r - dxr[t]);
-            } else {
-              acc[u] -= R * r;
-              Rlive[(size_t)q * ld + t] = R;
-            }
-            lam[u] += R * R;
-          }
+      for (int a = 0; a < VGM_ARITY; ++a) s[a] = X[(size_t)ode_idx[(size_t)j * VGM_ARITY + a] * ld + t];
+      double R, r;
+      vgm_state_coeffs(pair_code[e], th, s, R, r);
+      if (pair_self[e]) {
+        R_self = R;
+        r_self = r;
+      } else {
+        const int q = pair_live[e];
+        if (q < 0) {
+          acc -= R * (r - DX0[(size_t)ode_state[j] * ld + t]);
+        } else {
+          acc -= R * r;
+          Rlive[(size_t)q * ld + t] = R;
         }
+        lam += R * R;
       }
     }
-#pragma unroll
-    for (int u = 0; u < VGM_ASM_T; ++u) {
-      const int t = t0 + threadIdx.x + u * blockDim.x;
-      if (t < T) {
-        const size_t o = (size_t)i * ld + t;
-        Lambda[o] = lam[u];
-        rhs[o] = acc[u];
-        ruu[o] = r_self[u];
-        if (Ruu) Ruu[o] = R_self[u];
-      }
-    }
+    const size_t o = (size_t)i * ld + t;
+    Lambda[o] = lam;
+    rhs[o] = acc;
+    ruu[o] = r_self;
+    if (Ruu) Ruu[o] = R_self;
   }
 }
 
