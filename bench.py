@@ -425,6 +425,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer
+    is allocated: first-touch then places the e2e staging buffers on the GPU's own NUMA node.  torchrun does not do
+    this; without it half of the ranks copy across the socket interconnect.  Returns a short description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d (%d)" % (min(cpus), max(cpus), len(cpus))
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def native_arm(args):
     import ctypes as C
 
@@ -443,6 +463,8 @@ def native_arm(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -568,6 +590,14 @@ def native_arm(args):
                 core.iteration_host(Xh_in, th_h, Xh_out, updated_rows_only=True, pipeline_chunks=args.pipeline_chunks)
 
         e2e_step()
+        # what the host link gives this rank while every rank copies at once (context for the e2e figure)
+        barrier()
+        torch.cuda.synchronize()
+        tc0 = time.perf_counter()
+        for _ in range(3):
+            core.X.copy_(Xh_in, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * h2d / (time.perf_counter() - tc0) / 1e9
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -582,9 +612,12 @@ def native_arm(args):
             dt = float(tmax.item())
         e2e = {"value": n_hidden_total * T * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
+               "h2d_gbs_rank0_all_ranks_copying": h2d_gbs, "cpu_binding": numa,
                "api": ("vgm_iteration_host (C ABI, pinned host buffers; %d state ranges pipelined: copy-in, "
                        "solve and copy-out overlap)" % core.last_pipeline) if world == 1 else
                       "DistributedVGMEngine.iteration with pinned host copies per rank (all local rows in, updated rows out)"}
+
+    os.sched_setaffinity(0, full_affinity)       # the CPU checks / baseline below use every host core again
 
     # ---- parity of this very configuration against the oracle (every rank takes part in the gathers) ------
     parity = None

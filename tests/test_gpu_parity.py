@@ -354,6 +354,37 @@ def test_kernel_types_on_sqrt_of_squared_distance(pkg, ktype, kparam):
         gpr.kernel_function(t, t2, ktype, kparam)
 
 
+def test_gm_operators_batch_of_hyperparameter_sets(pkg):
+    """vgm_gm_operators(batch=3): three hyper-parameter sets (per-state phi_k; the reference has one shared phi,
+    GP_regression.py:306,317) processed back to back -- every set against the oracle's LU route."""
+    _, _lib, _ = pkg
+    lib = _lib.load()
+    T, ld = 150, 152
+    t = np.arange(T) * 0.05
+    sets = [("rbf", [0.0625, 1.0]), ("rbf", [0.07, 1.7]), ("RQ", [0.8, 0.09, 1.2])]
+    mats = [vo.kernel_matrices(t, t[:2], kt, kp)[:3] for kt, kp in sets]
+
+    def stack(i):
+        out = torch.zeros((3, T, ld), dtype=torch.float64, device="cuda")
+        for b in range(3):
+            out[b, :, :T] = torch.as_tensor(mats[b][i], device="cuda")
+        return out
+    Cm, dC, ddC = stack(0), stack(1), stack(2)
+    D, A, Ci = torch.zeros_like(Cm), torch.zeros_like(Cm), torch.zeros_like(Cm)
+    n = lib.vgm_gm_operators_ws_bytes(T, ld)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.vgm_gm_operators(Cm.data_ptr(), dC.data_ptr(), ddC.data_ptr(), T, ld, 3, D.data_ptr(), A.data_ptr(),
+                                    Ci.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for b in range(3):
+        Dr, Ar = vo.gm_operators(*mats[b])
+        tol = max(1e-12, 50 * np.linalg.cond(mats[b][0]) * 2.2e-16)
+        assert tol < TOL
+        assert relerr(D[b, :, :T].cpu().numpy(), Dr) < tol, b
+        assert relerr(A[b, :, :T].cpu().numpy(), Ar) < tol, b
+        assert relerr(Ci[b, :, :T].cpu().numpy(), np.linalg.inv(mats[b][0])) < tol, b
+
+
 def test_kernel_function_errors_like_the_reference(pkg):
     from variational_gradient_matching_for_dynamical_systems_b200 import GP_regression as gpr
     t = np.arange(8) * 0.1
