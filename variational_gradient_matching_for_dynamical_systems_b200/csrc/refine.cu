@@ -198,8 +198,11 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
-__global__ void __launch_bounds__(IR_THREADS) ir_dir_warp_kernel(IrBuf b, const int* __restrict__ n_dev, int n, int T,
-                                                                 int ld, int first) {
+// MINB = resident CTAs per SM the register allocation is capped for: the kernel is latency-bound (ncu: 3.7 active
+// warps per scheduler, 77 % of the stall cycles wait for loads), so more resident warps mean more loads in flight
+template <int MINB>
+__global__ void __launch_bounds__(IR_THREADS, MINB) ir_dir_warp_kernel(IrBuf b, const int* __restrict__ n_dev, int n, int T,
+                                                                       int ld, int first) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * (IR_THREADS / 32) + (threadIdx.x >> 5);
@@ -330,11 +333,18 @@ int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cu
   // reads acc32 4, s16 2, rsb 2, (p_hi, p_lo 4); writes p_hi, p_lo 4
   ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * (first ? 12.0 : 16.0), s);
   // VGM_IR_DIR_VARIANT=1: one CTA per row with the row in registers (like ir_update) instead of one warp per row
-  static const int variant = getenv("VGM_IR_DIR_VARIANT") ? atoi(getenv("VGM_IR_DIR_VARIANT")) : 0;
+  // default 3: register allocation capped for 3 resident CTAs per SM (85 registers, 24 bytes of spills): measured
+  // 5.65 ms per step at 0.86 of the HBM copy bandwidth against 6.09 ms / 0.80 with 2 CTAs (92 registers) and
+  // 5.76 ms with 4 (176 bytes of spills); 2 / 4 select those, 1 the CTA-per-row kernel (6.6 ms)
+  static const int variant = getenv("VGM_IR_DIR_VARIANT") ? atoi(getenv("VGM_IR_DIR_VARIANT")) : 3;
   if (variant == 1 && T <= 4 * IR_THREADS)
     VGM_CUDA_OK(launch_pdl(ir_dir_kernel<true>, dim3(n), dim3(IR_THREADS), 0, s, b, n_dev, T, ld, first));
-  else if (T <= 8 * 32 * IR_WG && (T % 8) == 0)
-    VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel, dim3(ceil_div(n, IR_THREADS / 32)), dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
+  else if (T <= 8 * 32 * IR_WG && (T % 8) == 0) {
+    const dim3 grid(ceil_div(n, IR_THREADS / 32));
+    if (variant == 2) VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<2>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
+    else if (variant == 4) VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<4>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
+    else VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<3>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
+  }
   else if (T <= 4 * IR_THREADS)
     VGM_CUDA_OK(launch_pdl(ir_dir_kernel<true>, dim3(n), dim3(IR_THREADS), 0, s, b, n_dev, T, ld, first));
   else
