@@ -187,6 +187,17 @@ int vgm_param_stats(const vgm_program* prog, const double* X, const double* DX, 
                     double* stats, void* ws, size_t ws_bytes, vgm_stream_t stream);
 int vgm_param_solve(const double* stats, int n_param, double* theta, vgm_stream_t stream);
 
+/* 'minimizer' parameter update (opt-in beyond the closed-form path; proxies...py:114-128 hands the squared
+ * gradient-matching loss of :379-392 to scipy.optimize.minimize).  One evaluation on the device:
+ *   out[0]     = sum_{k,t} (f_k(x(t), theta) - (D x_k)(t))^2
+ *   out[1 + i] = 2 sum_{k,t} (f_k - D x_k) d f_k / d theta_i          (the L2 penalty alpha |theta|^2 is the caller's)
+ * with f_k and its parameter gradient from the generated program, so models that are not linear in a parameter
+ * (Protein Transduction's K_m) have a GPU path too.  theta, out: device.  The optimiser stays SciPy's on the host. */
+size_t vgm_param_loss_ws_bytes(int n_odes, int n_param);
+int vgm_param_loss(const vgm_program* prog, const double* X, const double* DX, int ld, int T, int n_odes,
+                   const int* ode_class, const int* ode_idx, const int* ode_state, const double* theta, double* out,
+                   void* ws, size_t ws_bytes, vgm_stream_t stream);
+
 /* Opt-in parameter "covariance"  cov = sum_k B_k^T A B_k  (p x p, row-major, device), the quantity the
  * reference computes at proxies...py:79 and never returns.  A = eps_cov [T][ld].  The B rows are
  * materialised in chunks of ODE rows, multiplied by A with the DMMA GEMM and reduced deterministically. */

@@ -276,6 +276,27 @@ def theta_step(X, lin: Linearisation, D, A=None):
     return theta, m, Sc, Cth
 
 
+def squared_loss(theta, X, D, odes_sym, state_symbols, param_symbols, alpha=0.0):
+    """Loss and gradient of the 'minimizer' parameter update (proxies...py:379-392):
+    ``sum (f(X, theta) - D X)^2 + alpha |theta|^2`` and ``2 sum (f - D X) df/dtheta + 2 alpha theta``
+    (the reference's gradient_of_odes replaces exact-zero derivatives by machine epsilon, import_odes.py:45; that
+    changes the gradient by ~1e-16 relative and is not reproduced).  Returns (loss, grad)."""
+    X = np.asarray(X, dtype=float)
+    theta = np.asarray(theta, dtype=float)
+    DX = np.asarray(D).dot(X)
+    args = list(state_symbols) + list(param_symbols)
+    vals = [X[:, i] for i in range(X.shape[1])] + [float(v) for v in theta]
+    loss, grad = 0.0, np.zeros(len(theta))
+    for k, e in enumerate(odes_sym):
+        f = np.broadcast_to(sym.lambdify(args, e, "numpy")(*vals), (X.shape[0],))
+        res = f - DX[:, k]
+        loss += float(np.sum(res ** 2))
+        for i, ps in enumerate(param_symbols):
+            df = np.broadcast_to(sym.lambdify(args, sym.diff(e, ps), "numpy")(*vals), (X.shape[0],))
+            grad[i] += 2.0 * float(np.sum(res * df))
+    return loss + alpha * float(np.sum(theta ** 2)), grad + 2.0 * alpha * theta
+
+
 # --------------------------------------------------------------------------------------
 # P4: state sweep  (proxies...py:185-262)
 # --------------------------------------------------------------------------------------

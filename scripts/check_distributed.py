@@ -52,6 +52,13 @@ def main():
             ex = ((Xs - Xm).abs().max() / Xs.abs().max()).item()
             et = abs(single.get_theta()[0] - multi.get_theta()[0]) / abs(single.get_theta()[0])
             errs.append((ex, et))
+        # pooled 'minimizer' loss / gradient: sum over the ranks' ODE rows == single-GPU value
+        single.compute_DX()
+        multi.halo(multi.engine.X)
+        multi.engine.compute_DX()
+        ls, gs = single.param_loss([7.5], alpha=0.3)
+        lm, gm = multi.param_loss([7.5], alpha=0.3)
+        errs.append((0.0, max(abs(ls - lm) / abs(ls), float(np.max(np.abs(gs - gm)) / np.max(np.abs(gs))))))
         res[tag] = {"state_rel_err": max(e[0] for e in errs), "theta_rel_err": max(e[1] for e in errs),
                     "levels": multi.n_levels, "shift": multi.shift, "cross_rank_live": multi.cross_rank_live,
                     "tail_overlap_ranks": int(_sum_int(multi.engine.plan.c.n_early > 0, dev))}

@@ -823,6 +823,79 @@ def test_observation_sampler_follows_the_reference_noise_model(pkg):
     assert abs(float(z.mean())) < 0.08 and abs(float(z.std()) - 1.0) < 0.05
 
 
+@pytest.mark.parametrize("tag", ["lv", "pt6"])
+def test_param_loss_kernel_vs_live_reference(pkg, tag):
+    """vgm_param_loss (loss + gradient of the 'minimizer' parameter update) against the live reference's own
+    squared_loss / squared_loss_gradient (proxies...py:379-392; golden from oracle/make_golden_minimizer.py):
+    Lotka-Volterra and the SHIPPED six-parameter Protein Transduction model, which is not linear in _K_m."""
+    p, _lib, engine = pkg
+    g = load("minimizer_params.npz")
+    lines, names, params = ([str(x) for x in g[tag + "__" + k]] for k in ("lines", "names", "params"))
+    model = p.OdeModel(lines, names, params)
+    assert model.param_nonlinear == (tag == "pt6")
+    eng = engine.VGMEngine(model, g[tag + "__D"], None, hidden=[], theta_mode="proxy")
+    eng.set_states(g[tag + "__X0"])
+    eng.compute_DX()
+    x0 = 0.1 * np.ones(len(params))
+    loss, grad = eng.param_loss(x0)
+    assert abs(loss - float(g[tag + "__loss_x0"])) < 1e-11 * abs(float(g[tag + "__loss_x0"]))
+    assert relerr(grad, g[tag + "__grad_x0"]) < 1e-11
+    # shrinkage penalty (alpha = 0.3, proxies...py:122-123)
+    l2, g2 = eng.param_loss(x0, alpha=0.3)
+    assert abs(l2 - loss - 0.3 * np.sum(x0 ** 2)) < 1e-12 * abs(l2) and np.allclose(g2 - grad, 0.6 * x0, rtol=0, atol=1e-9)
+    if tag == "pt6":
+        with pytest.raises(Exception, match="(?i)nonlinear"):
+            eng.param_stats()                     # no closed-form update for this model, as in the reference
+
+
+def test_param_loss_builtin_lorenz96_vs_oracle(pkg):
+    import sympy as sym
+    p, _lib, engine = pkg
+    g = load("lorenz96_K10_T40.npz")
+    K = 10
+    names = ["_x_%d" % (i + 1) for i in range(K)]
+    eng = engine.VGMEngine(p.OdeModel.lorenz96(K), g["D"], None, hidden=list(range(1, K, 2)))
+    assert eng.program.kind == "builtin:lorenz96"
+    eng.set_states(g["X0"])
+    eng.compute_DX()
+    loss, grad = eng.param_loss([7.3])
+    st, pa = sym.symbols(names), sym.symbols(["_alpha"])
+    lo, go = vo.squared_loss([7.3], g["X0"], g["D"], vo.parse_ode_lines(vo.lorenz96_ode_lines(K)), st, pa)
+    assert abs(loss - lo) < 1e-12 * abs(lo) and relerr(grad, go) < 1e-12
+
+
+@pytest.mark.parametrize("tag", ["lv", "pt6"])
+@pytest.mark.parametrize("constraints", [None, "shrinkage", "nonnegative"])
+def test_minimizer_parameter_update_vs_live_reference(pkg, tag, constraints, tmp_path):
+    """proxy_for_ode_parameters(optimizer='minimizer') through the drop-in surface: the reference's SciPy calls with
+    the loss evaluated on the device, against the live reference's result.  Own tolerance (the minimiser's, not
+    1e-9): theta within 1e-4 relative, attained loss within 1e-8."""
+    import pandas as pd
+    import sympy as sym
+    from variational_gradient_matching_for_dynamical_systems_b200 import import_odes as io_
+    from variational_gradient_matching_for_dynamical_systems_b200 import proxies_for_ode_parameters_and_states as PX
+    g = load("minimizer_params.npz")
+    lines, names, params = ([str(x) for x in g[tag + "__" + k]] for k in ("lines", "names", "params"))
+    path = os.path.join(str(tmp_path), "m_ODEs.txt")
+    open(path, "w").write("\n".join(lines) + "\n")
+
+    class S:
+        state = sym.symbols(names)
+        param = sym.symbols(params)
+    odes, odes_sym = io_.import_odes(S, path)
+    sp = pd.DataFrame(g[tag + "__X0"], index=g[tag + "__t"], columns=names)
+    th = PX.proxy_for_ode_parameters(sp, None, g[tag + "__D"], None, S.param, None, odes, None, constraints, 'minimizer')
+    ref = g[tag + "__theta_" + str(constraints)]
+    assert list(th.index) == params and th.index.name == "ODE parameter symbols"
+    assert relerr(th.values.ravel(), ref) < 1e-4, (th.values.ravel(), ref)
+    eng = PX._engine_for_parameters(odes.model, g[tag + "__D"])
+    loss = eng.param_loss(th.values.ravel(), 0.3 if constraints == "shrinkage" else 0.0)[0]
+    ref_loss = float(g[tag + "__loss_" + str(constraints)])
+    assert abs(loss - ref_loss) < 1e-8 * abs(ref_loss)
+    if constraints == "nonnegative":
+        assert np.all(th.values.ravel() >= 0.0)
+
+
 def test_colour_schedule_at_K1000(pkg):
     """The opt-in colour schedule at config C3's size (K=1000, T=1000): two colours of 250 systems, converged hidden
     RMSE within 5 % of the reference order's (its own stated tolerance; north_star: reported separately)."""
@@ -913,8 +986,15 @@ def test_dropin_api_call_sequence_matches_reference_golden(pkg, tmp_path):
     with pytest.raises(ValueError, match="wrong shape"):
         PX.proxy_for_ode_parameters(state.iloc[:5], locally_linear_odes, dC_times_inv_C, eps_cov, symbols.param, None,
                                     odes, None, None, optimizer='analytical')
+    # the reference's default optimizer='minimizer' runs for the parameters (SciPy BFGS, loss on the device) ...
+    th_min = PX.proxy_for_ode_parameters(state, locally_linear_odes, dC_times_inv_C, eps_cov, symbols.param, None, odes, None)
+    th_ana = PX.proxy_for_ode_parameters(state, locally_linear_odes, dC_times_inv_C, eps_cov, symbols.param, None, odes,
+                                         None, None, optimizer='analytical')      # same least-squares problem for B == 1
+    assert list(th_min.index) == ["_alpha"] and abs(float(th_min.values[0, 0]) - float(th_ana.values[0, 0])) < 1e-5
+    # ... the 'minimizer' state update (SciPy L-BFGS-B per state, proxies...py:278-366) stays out of scope
     with pytest.raises(NotImplementedError):
-        PX.proxy_for_ode_parameters(state, locally_linear_odes, dC_times_inv_C, eps_cov, symbols.param, None, odes, None)
+        PX.proxy_for_ind_states(state, param, odes, None, locally_linear_odes, dC_times_inv_C, eps_cov, None, None,
+                                observations, None, state_couplings, optimizer='minimizer')
 
 
 def test_fitting_state_observations_vs_reference_golden(pkg):

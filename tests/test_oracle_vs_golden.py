@@ -226,3 +226,15 @@ def test_predictive_cov_is_what_the_reference_inverts():
     # P has singular values from 4 down to 1e-17: the pinv is only a Moore-Penrose inverse to ~1e-3 (rounding amplified by
     # the retained 1/s ~ 1e14), which is why parity on state_pred_inv_cov itself is not well posed
     assert np.linalg.norm(P @ G @ P - P) / np.linalg.norm(P) < 1e-2
+
+
+@pytest.mark.parametrize("tag", ["lv", "pt6"])
+def test_squared_loss_restatement_matches_live_reference(tag):
+    """oracle.squared_loss against the live reference's squared_loss / squared_loss_gradient at the minimiser's start
+    point (golden from oracle/make_golden_minimizer.py)."""
+    g = load("minimizer_params.npz")
+    lines, names, params = ([str(x) for x in g[tag + "__" + k]] for k in ("lines", "names", "params"))
+    lo, go = vo.squared_loss(0.1 * np.ones(len(params)), g[tag + "__X0"], g[tag + "__D"], vo.parse_ode_lines(lines),
+                             sym.symbols(names), sym.symbols(params))
+    assert abs(lo - float(g[tag + "__loss_x0"])) < 1e-12 * abs(lo)
+    assert relerr(go, g[tag + "__grad_x0"]) < 1e-11

@@ -121,6 +121,9 @@ SIGNATURES = {
     "vgm_param_stats_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vgm_param_stats": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp,
                                   C.c_size_t, C.c_void_p]),
+    "vgm_param_loss_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "vgm_param_loss": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp, c_dp,
+                                 C.c_size_t, C.c_void_p]),
     "vgm_param_solve": (C.c_int, [c_dp, C.c_int, c_dp, C.c_void_p]),
     "vgm_param_cov_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vgm_param_cov": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_dp, c_dp, C.c_size_t,

@@ -271,7 +271,22 @@ class OdeModel:
                     continue
                 out.append("    case %d: { R = %s; r = %s; } break;" % (
                     int(self.code_base[ci]) + j, _ccode(c.R[j], subs), _ccode(c.r[j], subs)))
-        out += ["    default: { R = 0.0; r = 0.0; } break;", "  }", "}", ""]
+        out += ["    default: { R = 0.0; r = 0.0; } break;", "  }", "}",
+                "__device__ __forceinline__ void vgm_ode_eval(int cls, const double* th, const double (&s)[VGM_ARITY], "
+                "double& f, double (&df)[VGM_NPARAM]) {",
+                "  switch (cls) {"]
+        for ci, c in enumerate(self.classes):
+            subs = {ph: sym.Symbol("s[%d]" % j) for j, ph in enumerate(c.placeholders)}
+            subs.update(subs_all)
+            out.append("    case %d: {" % ci)
+            out.append("      f = %s;" % _ccode(c.expr, subs))
+            for i, ps in enumerate(self.param_symbols):
+                out.append("      df[%d] = %s;" % (i, _ccode(sym.diff(c.expr, ps), subs)))     # import_odes.py:40-47
+            out.append("    } break;")
+        out.append("    default: {")
+        for i in range(self.p):
+            out.append("      df[%d] = 0.0;" % i)
+        out += ["      f = 0.0;", "    } break;", "  }", "}", ""]
         with open(_TEMPLATE) as f:
             out.append(f.read())
         return "\n".join(out)

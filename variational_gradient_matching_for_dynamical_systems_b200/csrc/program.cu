@@ -29,6 +29,10 @@ __device__ __forceinline__ void vgm_state_coeffs(int code, const double* th, con
     default: R = -1.0;        r = a + s[0] * s[2] - s[1] * s[2]; break;   // u = k
   }
 }
+__device__ __forceinline__ void vgm_ode_eval(int, const double* th, const double (&s)[4], double& f, double (&df)[1]) {
+  f = (s[0] - s[1]) * s[2] - s[3] + th[0];
+  df[0] = 1.0;
+}
 #include "vgm_program_template.cuh"
 #undef VGM_PROG
 #undef VGM_NPARAM
@@ -44,6 +48,7 @@ struct vgm_program {
   cudaKernel_t k_assemble;
   cudaKernel_t k_pair_R;
   cudaKernel_t k_param_B;
+  cudaKernel_t k_param_loss;
 };
 
 namespace vgm {
@@ -94,6 +99,23 @@ int program_param_stats(const vgm_program* prog, const double* X, const double* 
   void* args[] = {(void*)&X, (void*)&DX, (void*)&ld, (void*)&T, (void*)&n_odes, (void*)&ode_class,
                   (void*)&ode_idx, (void*)&ode_state, (void*)&partial};
   return driver_launch(prog->k_stats, grid, block, args, s);
+}
+
+int program_param_loss(const vgm_program* prog, const double* X, const double* DX, int ld, int T, int n_odes,
+                       const int* ode_class, const int* ode_idx, const int* ode_state, const double* theta,
+                       double* partial, cudaStream_t s) {
+  const int grid = ceil_div(n_odes, 8);
+  const int block = prog_threads(T);
+  ProfScope prof(PROF_ASSEMBLE, 0.0, 16.0 * n_odes * T, s);
+  if (prog->builtin) {
+    lorenz96_prog::vgm_lorenz96_param_loss<<<grid, block, 0, s>>>(X, DX, ld, T, n_odes, ode_class, ode_idx, ode_state,
+                                                                  theta, partial);
+    VGM_LAUNCH_OK();
+    return VGM_OK;
+  }
+  void* args[] = {(void*)&X, (void*)&DX, (void*)&ld, (void*)&T, (void*)&n_odes, (void*)&ode_class,
+                  (void*)&ode_idx, (void*)&ode_state, (void*)&theta, (void*)&partial};
+  return driver_launch(prog->k_param_loss, grid, block, args, s);
 }
 
 int program_param_B(const vgm_program* prog, const double* X, int ld, int T, int n_rows, const int* ode_class,
@@ -251,6 +273,7 @@ extern "C" int vgm_program_builtin(const char* name, vgm_program** out) {
   p->k_assemble = nullptr;
   p->k_pair_R = nullptr;
   p->k_param_B = nullptr;
+  p->k_param_loss = nullptr;
   *out = p;
   return VGM_OK;
 }
@@ -273,6 +296,7 @@ extern "C" int vgm_program_load(const void* cubin_host, size_t size, int n_param
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->k_assemble, p->lib, "vgm_prog_state_assemble");
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->k_pair_R, p->lib, "vgm_prog_state_pair_R");
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->k_param_B, p->lib, "vgm_prog_param_B");
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->k_param_loss, p->lib, "vgm_prog_param_loss");
   if (e != cudaSuccess) {
     set_error("cudaLibraryGetKernel: %s", cudaGetErrorString(e));
     cudaLibraryUnload(p->lib);
@@ -291,6 +315,25 @@ extern "C" int vgm_program_free(vgm_program* prog) {
 }
 
 extern "C" int vgm_program_n_param(const vgm_program* prog) { return prog ? prog->n_param : -1; }
+
+// 'minimizer' parameter update: out = [loss | gradient (p)] on the device (deterministic two-pass reduction)
+extern "C" size_t vgm_param_loss_ws_bytes(int n_odes, int n_param) {
+  return align_up((size_t)ceil_div(n_odes, 8) * (n_param + 1) * sizeof(double), 256);
+}
+
+extern "C" int vgm_param_loss(const vgm_program* prog, const double* X, const double* DX, int ld, int T, int n_odes,
+                              const int* ode_class, const int* ode_idx, const int* ode_state, const double* theta,
+                              double* out, void* ws, size_t ws_bytes, vgm_stream_t stream) {
+  VGM_REQUIRE(prog && X && DX && ode_class && ode_idx && ode_state && theta && out && ws, "null argument");
+  VGM_REQUIRE(n_odes > 0 && T > 0 && ld >= T, "shape");
+  VGM_REQUIRE(ws_bytes >= vgm_param_loss_ws_bytes(n_odes, prog->n_param), "workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  double* partial = (double*)ws;
+  VGM_TRY(program_param_loss(prog, X, DX, ld, T, n_odes, ode_class, ode_idx, ode_state, theta, partial, s));
+  cov_reduce_kernel<<<1, 256, 0, s>>>(partial, ceil_div(n_odes, 8), prog->n_param + 1, out);
+  VGM_LAUNCH_OK();
+  return VGM_OK;
+}
 
 extern "C" size_t vgm_param_stats_ws_bytes(int n_odes, int T, int n_param) {
   (void)T;

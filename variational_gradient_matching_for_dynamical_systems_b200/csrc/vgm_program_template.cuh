@@ -11,6 +11,7 @@
 //   #define VGM_ARITY  <a>                        max #states referenced by one ODE
 //   __device__ void vgm_theta_coeffs(int cls, const double (&s)[VGM_ARITY], double (&B)[VGM_NPARAM], double& b);
 //   __device__ void vgm_state_coeffs(int code, const double* th, const double (&s)[VGM_ARITY], double& R, double& r);
+//   __device__ void vgm_ode_eval(int cls, const double* th, const double (&s)[VGM_ARITY], double& f, double (&df)[VGM_NPARAM]);
 //
 // Layout: X, DX, Lambda, rhs, ... are [rows][ld] FP64 with the time index contiguous, so a
 // warp reads/writes 256 contiguous bytes per row (coalesced, 8-byte lanes).
@@ -71,6 +72,57 @@ VGM_PROG(param_stats)(const double* __restrict__ X, const double* __restrict__ D
     double v = 0.0;
     for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) v += red[ww][i];
     partial[(size_t)blockIdx.x * VGM_NSTAT + i] = v;
+  }
+}
+
+// 'minimizer' parameter update (opt-in; proxies_for_ode_parameters_and_states.py:114-128 minimises the loss of
+// :379-392 with SciPy): per-CTA partials of
+//   partial[cta][0]     = sum_{k,t} (f_k(x(t), theta) - (D x_k)(t))^2
+//   partial[cta][1 + i] = 2 sum_{k,t} (f_k - D x_k) d f_k / d theta_i
+// f_k and its parameter gradient come from the generated vgm_ode_eval, so models that are NOT linear in a parameter
+// (Protein Transduction's K_m) are covered.
+extern "C" __global__ void __launch_bounds__(VGM_PROG_THREADS)
+VGM_PROG(param_loss)(const double* __restrict__ X, const double* __restrict__ DX, int ld, int T, int n_odes,
+                     const int* __restrict__ ode_class, const int* __restrict__ ode_idx,
+                     const int* __restrict__ ode_state, const double* __restrict__ theta,
+                     double* __restrict__ partial) {
+  double th[VGM_NPARAM], acc[VGM_NPARAM + 1];
+#pragma unroll
+  for (int i = 0; i < VGM_NPARAM; ++i) th[i] = theta[i];
+#pragma unroll
+  for (int i = 0; i <= VGM_NPARAM; ++i) acc[i] = 0.0;
+  const int j0 = blockIdx.x * VGM_STAT_ROWS;
+  for (int jj = 0; jj < VGM_STAT_ROWS; ++jj) {
+    const int j = j0 + jj;
+    if (j >= n_odes) break;
+    const int cls = ode_class[j];
+    const double* dxrow = DX + (size_t)ode_state[j] * ld;
+    const double* xr[VGM_ARITY];
+#pragma unroll
+    for (int a = 0; a < VGM_ARITY; ++a) xr[a] = X + (size_t)ode_idx[(size_t)j * VGM_ARITY + a] * ld;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      double s[VGM_ARITY], f, df[VGM_NPARAM];
+#pragma unroll
+      for (int a = 0; a < VGM_ARITY; ++a) s[a] = xr[a][t];
+      vgm_ode_eval(cls, th, s, f, df);
+      const double e = f - dxrow[t];
+      acc[0] += e * e;
+#pragma unroll
+      for (int i = 0; i < VGM_NPARAM; ++i) acc[1 + i] += 2.0 * e * df[i];
+    }
+  }
+  __shared__ double red[VGM_PROG_THREADS / 32][VGM_NPARAM + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i <= VGM_NPARAM; ++i) {
+    const double v = vgm_prog_warp_sum(acc[i]);
+    if (lane == 0) red[w][i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= VGM_NPARAM; i += blockDim.x) {
+    double v = 0.0;
+    for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) v += red[ww][i];
+    partial[(size_t)blockIdx.x * (VGM_NPARAM + 1) + i] = v;
   }
 }
 

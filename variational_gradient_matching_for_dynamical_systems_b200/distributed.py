@@ -372,5 +372,17 @@ class DistributedVGMEngine:
             e.param_solve()
         return e.last_info
 
+    def param_loss(self, theta, alpha=0.0):
+        """Pooled loss and gradient of the 'minimizer' parameter update (``VGMEngine.param_loss``) over all ranks:
+        every rank evaluates its own ODE rows, one all-reduce of 1 + p doubles.  D.X must be current on every rank
+        (``engine.compute_DX`` after a halo refresh)."""
+        e = self.engine
+        loss, grad = e.param_loss(theta, 0.0)
+        buf = torch.as_tensor(np.concatenate([[loss], grad]), device=e.dev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        out = buf.cpu().numpy()
+        th = np.asarray(theta, dtype=np.float64).ravel()
+        return float(out[0] + alpha * np.sum(th ** 2)), out[1:] + 2.0 * alpha * th
+
     def get_theta(self):
         return self.engine.get_theta()

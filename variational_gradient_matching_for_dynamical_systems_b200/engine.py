@@ -475,6 +475,25 @@ class VGMEngine:
                                             self.stats.data_ptr(), self.ws.data_ptr(), n, _lib.stream_ptr()))
         return self.stats
 
+    def param_loss(self, theta, alpha=0.0):
+        """Squared gradient-matching loss of the 'minimizer' parameter update and its gradient
+        (proxies...py:379-392): ``sum (f(X, theta) - D X)^2 + alpha |theta|^2`` on the current states; D.X must be
+        current (``compute_DX``).  Works for models that are not linear in their parameters.  Returns (loss, grad)."""
+        th = torch.as_tensor(np.array(theta, dtype=np.float64, copy=True).ravel(), device=self.dev)
+        if th.numel() != self.p:
+            raise ValueError("theta must have %d entries" % self.p)
+        n_odes = self.problem.n_stats_odes
+        n = self.lib.vgm_param_loss_ws_bytes(n_odes, self.p)
+        if getattr(self, "_loss_ws", None) is None or self._loss_ws.numel() < n:
+            self._loss_ws = torch.empty(max(n, 256), dtype=torch.uint8, device=self.dev)
+            self._loss_out = torch.zeros(self.p + 1, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.vgm_param_loss(self.program.handle, self.X.data_ptr(), self.DX.data_ptr(), self.ld, self.T,
+                                           n_odes, self._mt.ode_class, self._mt.ode_idx, self._mt.ode_state, th.data_ptr(),
+                                           self._loss_out.data_ptr(), self._loss_ws.data_ptr(), n, _lib.stream_ptr()))
+        out = self._loss_out.cpu().numpy()
+        thn = th.cpu().numpy()
+        return float(out[0] + alpha * np.sum(thn ** 2)), out[1:] + 2.0 * alpha * thn
+
     def param_solve(self):
         _lib.check(self.lib.vgm_param_solve(self.stats.data_ptr(), self.p, self.theta.data_ptr(), _lib.stream_ptr()))
         return self.theta

@@ -4,9 +4,11 @@ the two coordinate-ascent updates with their verbatim signatures, computed on th
 * ``proxy_for_ode_parameters``  <- proxies_for_ode_parameters_and_states.py:41-139
 * ``proxy_for_ind_states``      <- proxies_for_ode_parameters_and_states.py:159-375
 
-Scope: ``optimizer='analytical'`` -- the closed-form Gaussian updates.
-``optimizer='minimizer'`` (SciPy BFGS on a squared loss) is third-party arithmetic outside the
-B200 path and raises ``NotImplementedError``.  Plotting side effects are omitted.
+Scope: ``optimizer='analytical'`` -- the closed-form Gaussian updates -- for both functions.
+``proxy_for_ode_parameters(optimizer='minimizer')`` keeps the reference's SciPy optimiser calls
+and evaluates the squared gradient-matching loss and its gradient (:379-392) on the device, which also covers models
+that are not linear in a parameter; its tolerance is the minimiser's.  The 'minimizer' STATE update (:278-366, SciPy
+L-BFGS-B per state) raises ``NotImplementedError``.  Plotting side effects are omitted.
 
 Reference behaviours that are reproduced on purpose:
 
@@ -70,6 +72,18 @@ def _model_of(locally_linear_odes):
                     "rewrite_odes_as_linear_combination_in_parameters / _in_states")
 
 
+def _model_of_any(locally_linear_odes, odes):
+    """The model for the 'minimizer' path: from the rewrites when they exist, else from ``odes`` (import_odes); a
+    model that is not linear in its parameters has no parameter rewrite but still has a loss."""
+    try:
+        return _model_of(locally_linear_odes)
+    except TypeError:
+        model = getattr(odes, "model", None)
+        if model is None:
+            raise
+        return model
+
+
 def _engine(model, D, A, hidden, couplings, theta_mode, obs_inv_cov=None):
     key = (_model_key(model), _fingerprint(D), tuple(hidden), _couplings_key(couplings), theta_mode,
            float(settings.theta_literal), settings.tol, settings.solver, settings.schedule,
@@ -106,13 +120,33 @@ def proxy_for_ode_parameters(state_proxy, locally_linear_odes, dC_times_inv_C, e
         raise ValueError('Either state_proxy or dC_times_invC have the wrong shape')
     elif dC_times_inv_C.shape[0] != dC_times_inv_C.shape[1]:
         raise ValueError('dC_times_invC is not a square matrix')
-    if optimizer != 'analytical':
-        raise NotImplementedError("optimizer=%r: only the closed-form 'analytical' update runs on the B200 path "
-                                  "(the SciPy 'minimizer' branch, proxies...py:114-128, is out of scope)" % (optimizer,))
-    model = _model_of(locally_linear_odes)
+    if optimizer not in ('analytical', 'minimizer'):
+        raise NotImplementedError("optimizer=%r" % (optimizer,))
+    model = _model_of(locally_linear_odes) if optimizer == 'analytical' else _model_of_any(locally_linear_odes, odes)
     eng = _engine_for_parameters(model, dC_times_inv_C)          # reuses the sweep engine when there is one
     eng.set_states(np.asarray(state_proxy.values, dtype=np.float64))
     eng.compute_DX()
+    if optimizer == 'minimizer':
+        # proxies...py:114-128: the reference hands squared_loss / squared_loss_gradient (:379-392) to SciPy.  Same
+        # optimiser calls here (BFGS without bounds, L-BFGS-B with them, same start 0.1 or `init`), the loss and its
+        # gradient evaluated on the device (vgm_param_loss).  Own tolerance: the minimiser's, not 1e-9.
+        from scipy.optimize import minimize
+        x0 = 0.1 * np.ones(len(ode_param_symbols)) if init is None else np.asarray(init, dtype=np.float64)
+        if constraints not in (None, 'shrinkage', 'nonnegative'):
+            raise UnboundLocalError("cannot access local variable 'global_mean' where it is not associated with a value "
+                                    "(constraints=%r has no 'minimizer' branch in the reference)" % (constraints,))
+        alpha = 0.3 if constraints == 'shrinkage' else 0.0
+        cache = {}
+
+        def both(th):
+            key = th.tobytes()
+            if cache.get("k") != key:
+                cache["k"], cache["v"] = key, eng.param_loss(th, alpha)
+            return cache["v"]
+        kw = {"bounds": tuple([(0, None)] * len(x0))} if constraints == 'nonnegative' else {}
+        global_mean = minimize(lambda th: both(th)[0], x0, jac=lambda th: both(th)[1], **kw).x
+        return pd.DataFrame(global_mean, columns=['value'], index=map(str, ode_param_symbols)).rename_axis(
+            'ODE parameter symbols')
     stats = eng.param_stats().cpu().numpy()
     p = model.p
     local_mean, local_scaling = stats[:p], stats[p:].reshape(p, p)
