@@ -493,13 +493,14 @@ def test_host_buffer_iteration_matches_reference_golden(pkg, rows_only):
 
 @pytest.mark.parametrize("rows_only", [False, True])
 @pytest.mark.parametrize("chunks", [2, 4])
-def test_pipelined_host_iteration_matches_plain_and_oracle(pkg, chunks, rows_only):
+@pytest.mark.parametrize("T", [160, 192])
+def test_pipelined_host_iteration_matches_plain_and_oracle(pkg, chunks, rows_only, T):
     """vgm_iteration_host with the copies pipelined against the compute (chunked states, coefficients assembled one
     chunk ahead, the cyclic seam solved last): identical theta (same partial-sum layout) and states to 1e-12 of the
     unpipelined call, 1e-9 of the oracle."""
     p, _lib, engine = pkg
-    K, T = 96, 160
-    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=21)
+    K = 96                  # T = 160: direct per-CTA solver, ranges one after the other; T = 192: mixed-precision solver,
+    t, Xtrue = vo.lorenz96_trajectory(K, T, 0.05, seed=21)    # all ranges at once on their own streams (ir_solve_ranges)
     rng = np.random.default_rng(22)
     X0 = Xtrue.copy()
     X0[:, 1::2] += 0.5 * rng.standard_normal((T, K // 2))
@@ -508,6 +509,7 @@ def test_pipelined_host_iteration_matches_plain_and_oracle(pkg, chunks, rows_onl
     Xref = vo.lorenz96_state_sweep(X0, 8.0, D, hidden)
     th_ref = vo.lorenz96_theta_step(X0, D)[0]
     eng = engine.VGMEngine(p.OdeModel.lorenz96(K), D, A, hidden=hidden)
+    assert eng.solver == ("dense" if T <= 160 else "mixed")
     Xh = torch.zeros((eng.K, eng.ld), dtype=torch.float64).pin_memory()
     Xh[:, :T] = torch.from_numpy(np.ascontiguousarray(X0.T))
     res = {}
