@@ -117,12 +117,24 @@ def live_reference_record():
         return None
 
 
+def workload_config(K, T, n_gpus):
+    """`config` of the JSON line: the SAME dict in the native arm and in the reference (CPU) arm -- it names the
+    workload; what is specific to one arm's run goes under `details` (native) or `cpu_baseline.sample` (CPU)."""
+    K_h = K // 2
+    ld = (T + 127) // 128 * 128 if T >= 512 else (T + 7) // 8 * 8
+    return {"workload": "Lorenz96 K=%d states (%d hidden, every second state observed+clamped), T=%d; one step = "
+                        "analytical theta update + full state sweep from the same initial proxies" % (K, K_h, T),
+            "kernel": KERNEL, "dt": DT, "parallelism": "state-block x%d" % n_gpus,
+            "l2": "inputs larger than L2: each state-shaped FP64 array of the solve (X, P, Q, R, Z) is %.0f MB per GPU "
+                  "(126 MB of L2)" % (K_h / n_gpus * ld * 8 / 1e6)}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count()
-    steps, warmup = max(1, args.steps), min(args.warmup, 1)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     Ks = args.cpu_sample_K
     value, total, blas = cpu_port_run(Ks, args.T, steps, warmup)
     sample = ("Lorenz96 K=%d (%d hidden), T=%d: %d iteration(s) of the oracle port of the reference's analytical "
@@ -131,8 +143,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Lorenz96 K=%d T=%d, bounded CPU sample K=%d" % (args.K, args.T, Ks),
-                       "kernel": KERNEL, "dt": DT},
+            "config": workload_config(args.K, args.T, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "blas": blas, "live_reference": live_reference_record(),
                              "note": "this arm times the ORACLE PORT of the reference's algorithm (one dense LAPACK solve "
@@ -709,21 +720,16 @@ def native_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Lorenz96 K=%d states (%d hidden, every second state observed+clamped), T=%d; "
-                                   "one step = analytical theta update + full state sweep from the same initial "
-                                   "proxies" % (K, K_h, T),
-                       "kernel": KERNEL, "dt": DT,
-                       "solver": ("mixed precision (tol %g): FP64 residuals on the DMMA pipe, FP32 PCG corrections "
+            "config": workload_config(K, T, world),
+            "details": {"solver": ("mixed precision (tol %g): FP64 residuals on the DMMA pipe, FP32 PCG corrections "
                                   "(%d steps each) with bf16-split tcgen05 operator products" % (args.tol, args.inner_iters))
-                       if core.solver == "mixed" else
-                       ("FP64 PCG (tol %g) on the DMMA pipe, preconditioner %s" %
-                        (args.tol, "none" if args.no_precondition else "(M+shift I)^-1")),
-                       "bands": {"D": core.ops.band_D, "M": core.ops.band_M, "M_bf16": core.ops.band_M_lp,
-                                 "G_bf16": core.ops.band_G},
-                       "parallelism": "state-block x%d" % world,
-                       "l2": "inputs larger than L2 (X, P, Q, R, Z are %.0f MB each per GPU)" %
-                             (n_hidden_local * core.ld * 8 / 1e6),
-                       "profiled_ms_per_step": (ms_prof / args.steps) if ms_prof else None},
+                        if core.solver == "mixed" else
+                        ("FP64 PCG (tol %g) on the DMMA pipe, preconditioner %s" %
+                         (args.tol, "none" if args.no_precondition else "(M+shift I)^-1")),
+                        "bands": {"D": core.ops.band_D, "M": core.ops.band_M, "M_bf16": core.ops.band_M_lp,
+                                  "G_bf16": core.ops.band_G},
+                        "state_array_mb_per_gpu": n_hidden_local * core.ld * 8 / 1e6,
+                        "profiled_ms_per_step": (ms_prof / args.steps) if ms_prof else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "c4": c4, "colour_schedule": colour, "gpu_launches": launches,
             "clocks": clocks,
             "solver_iterations": pcg_iters, "theta": theta, "setup_s": setup_s,
