@@ -199,7 +199,7 @@ def test_mixed_precision_solver_matches_fp64_pcg_and_oracle(pkg):
     assert relerr(res["mixed"][0], res["pcg"][0]) < 1e-10
 
 
-@pytest.mark.parametrize("T,ell", [(1100, 0.0625), (1000, 0.1), (250, 0.0625)])
+@pytest.mark.parametrize("T,ell", [(1100, 0.0625), (1000, 0.1), (250, 0.0625), (1001, 0.0625), (515, 0.0625)])
 def test_mixed_solver_other_shapes_vs_oracle(pkg, T, ell):
     """Shapes off the benchmark's beaten path: T > 1024 (vector kernels keep the row in shared memory instead of
     registers), T not a multiple of 8, and a longer length scale (l = 2 dt: wider bands, cond(A) beyond the reach of
