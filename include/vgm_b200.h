@@ -279,6 +279,11 @@ int vgm_split_bf16(const double* in, void* out_bf16x2, int rows, int ld, vgm_str
  * A*: [n_rows][lda] bf16, B*: [M][ldb] bf16, out: [n_rows][ldo] fp32; band as in vgm_gemm_args. */
 int vgm_tc_gemm_bf16(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1, int M, int K,
                      int ldb, int band, float* out, int ldo, vgm_stream_t stream);
+/* The same product with the FP32 accumulators rounded to bf16 in the epilogue, out: [n_rows][ldo] bf16 (half the
+ * output bytes; the solver stores the preconditioner product z' = (s o r) G^T this way).  The output moves in
+ * 16-byte pieces: columns M .. round_up(M, 8) - 1 of a row are overwritten with zeros when M is not a multiple of 8. */
+int vgm_tc_gemm_bf16_out(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1, int M, int K,
+                         int ldb, int band, void* out_bf16, int ldo, vgm_stream_t stream);
 
 typedef struct {
   double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)                     */

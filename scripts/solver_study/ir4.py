@@ -26,9 +26,14 @@ S=bf16(np.sqrt((sh+c)/(Lam+c)))
 def mm(a,b): return (a.astype(f32)@b.astype(f32).T)
 def op_lp(ph,pl): return mm(ph,Mh_main)+mm(pl,Mh_corr)+mm(ph,Ml_corr)+Lam32*(ph+pl)
 RZB=int(sys.argv[4])
+import os
+ZB16=os.environ.get('ZB16')=='1'   # experiment: store z' = G (s o r) as bf16 instead of FP32
+def gz(rs):
+    a=mm(rs,Gb)
+    return bf16(a) if ZB16 else a
 def inner_pcg(r0, nit):
     r=r0.astype(f32).copy(); d=np.zeros_like(r)
-    rs=bf16(S*r); acc=mm(rs,Gb); z=S*acc
+    rs=bf16(S*r); acc=gz(rs); z=S*acc
     rz=np.sum((rs*acc) if RZB else (r*z),1,dtype=np.float64)
     ph,pl=split(z); p=ph+pl
     for it in range(nit):
@@ -36,7 +41,7 @@ def inner_pcg(r0, nit):
         pq=np.sum(p*q,1,dtype=np.float64)
         al=(rz/pq).astype(f32)[:,None]
         d+=al*p; r=r-al*q
-        rs=bf16(S*r); acc=mm(rs,Gb); z=S*acc
+        rs=bf16(S*r); acc=gz(rs); z=S*acc
         rzn=np.sum((rs*acc) if RZB else (r*z),1,dtype=np.float64)
         be=(rzn/rz).astype(f32)[:,None]
         p=z+be*p; ph,pl=split(p); p=ph+pl; rz=rzn

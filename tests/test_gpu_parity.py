@@ -173,6 +173,16 @@ def test_tcgen05_gemm_matches_fp32_reference(pkg, n, T, band, split):
     if split:
         exact = d(P) @ d(Bm).t()
         assert float((d(out[:, :T]) - exact).abs().max()) / scale < 1e-4
+    # bf16 output (the solver stores the preconditioner product this way): the same accumulators, rounded once
+    out16 = torch.full((n, ld), 512.0, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.vgm_tc_gemm_bf16_out(a0.data_ptr(), a1.data_ptr() if split else None, n, ld, b0.data_ptr(),
+                                        b1.data_ptr() if split else None, T, T, ld, band, out16.data_ptr(), ld, None))
+    torch.cuda.synchronize()
+    # TMA stores whole 16-byte pieces: with 2-byte elements the columns up to the next multiple of 8 are written (as
+    # zeros) when T is not one; the solver uses this output only for T % 8 == 0
+    assert bool((out16[:, (T + 7) // 8 * 8:] == 512.0).all()), "row padding was written"
+    assert T % 8 != 0 or bool((out16[:, T:] == 512.0).all())
+    assert torch.equal(out16[:, :T], out[:, :T].to(torch.bfloat16))
 
 
 def test_mixed_precision_solver_matches_fp64_pcg_and_oracle(pkg):

@@ -202,7 +202,7 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) {
 // warps per scheduler, 77 % of the stall cycles wait for loads), so more resident warps mean more loads in flight
 template <int MINB>
 __global__ void __launch_bounds__(IR_THREADS, MINB) ir_dir_warp_kernel(IrBuf b, const int* __restrict__ n_dev, int n, int T,
-                                                                       int ld, int first) {
+                                                                       int ld, int first, int zb16) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * (IR_THREADS / 32) + (threadIdx.x >> 5);
@@ -216,7 +216,13 @@ __global__ void __launch_bounds__(IR_THREADS, MINB) ir_dir_warp_kernel(IrBuf b, 
     const int i = 8 * (lane + 32 * g);
     z[g].a = z[g].b = pp[g].a = pp[g].b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < T) {                                              // T % 8 == 0: whole groups only
-      const float4 a0 = ld_f4(b.acc32 + o + i), a1 = ld_f4(b.acc32 + o + i + 4);
+      float4 a0, a1;                                         // z' = the preconditioner GEMM's output
+      if (zb16) {                                            // stored as bf16 rows (same ld) at the start of acc32
+        const f8 av = ld_bf8(reinterpret_cast<const __nv_bfloat16*>(b.acc32) + o + i);
+        a0 = av.a; a1 = av.b;
+      } else {
+        a0 = ld_f4(b.acc32 + o + i); a1 = ld_f4(b.acc32 + o + i + 4);
+      }
       const f8 sv = ld_bf8(b.s16 + o + i);
       const f8 rs = ld_bf8(b.rsb + o + i);                   // r.z = (s o r).acc, with the rounded s o r the GEMM saw
       if (!first) {
@@ -328,22 +334,34 @@ int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const d
   return VGM_OK;
 }
 
-int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s) {
-  if (n <= 0) return VGM_OK;
-  // reads acc32 4, s16 2, rsb 2, (p_hi, p_lo 4); writes p_hi, p_lo 4
-  ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * (first ? 12.0 : 16.0), s);
-  // VGM_IR_DIR_VARIANT=1: one CTA per row with the row in registers (like ir_update) instead of one warp per row
+static int ir_dir_variant() {
   // default 3: register allocation capped for 3 resident CTAs per SM (85 registers, 24 bytes of spills): measured
   // 5.65 ms per step at 0.86 of the HBM copy bandwidth against 6.09 ms / 0.80 with 2 CTAs (92 registers) and
   // 5.76 ms with 4 (176 bytes of spills); 2 / 4 select those, 1 the CTA-per-row kernel (6.6 ms)
   static const int variant = getenv("VGM_IR_DIR_VARIANT") ? atoi(getenv("VGM_IR_DIR_VARIANT")) : 3;
+  return variant;
+}
+
+// true when ir_dir runs the warp-per-row kernel, which can take the preconditioner product as bf16
+bool ir_dir_takes_bf16(int T) {
+  static const bool off = getenv("VGM_Z_FP32") != nullptr;
+  return !off && ir_dir_variant() != 1 && T <= 8 * 32 * IR_WG && (T % 8) == 0;
+}
+
+int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, int zb16, cudaStream_t s) {
+  if (n <= 0) return VGM_OK;
+  VGM_REQUIRE(!zb16 || ir_dir_takes_bf16(T), "ir_dir: bf16 accumulators need the warp-per-row kernel");
+  // reads acc 4 (2 as bf16), s16 2, rsb 2, (p_hi, p_lo 4); writes p_hi, p_lo 4
+  ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * ((first ? 12.0 : 16.0) - (zb16 ? 2.0 : 0.0)), s);
+  // VGM_IR_DIR_VARIANT=1: one CTA per row with the row in registers (like ir_update) instead of one warp per row
+  const int variant = ir_dir_variant();
   if (variant == 1 && T <= 4 * IR_THREADS)
     VGM_CUDA_OK(launch_pdl(ir_dir_kernel<true>, dim3(n), dim3(IR_THREADS), 0, s, b, n_dev, T, ld, first));
   else if (T <= 8 * 32 * IR_WG && (T % 8) == 0) {
     const dim3 grid(ceil_div(n, IR_THREADS / 32));
-    if (variant == 2) VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<2>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
-    else if (variant == 4) VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<4>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
-    else VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<3>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
+    if (variant == 2) VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<2>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first, zb16));
+    else if (variant == 4) VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<4>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first, zb16));
+    else VGM_CUDA_OK(launch_pdl(ir_dir_warp_kernel<3>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first, zb16));
   }
   else if (T <= 4 * IR_THREADS)
     VGM_CUDA_OK(launch_pdl(ir_dir_kernel<true>, dim3(n), dim3(IR_THREADS), 0, s, b, n_dev, T, ld, first));

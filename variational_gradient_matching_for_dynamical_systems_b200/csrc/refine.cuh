@@ -25,7 +25,9 @@ void ir_carve(char*& p, int n, int ld, IrBuf& b);
 int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const double* rr, const int* act, int n,
                   const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s);
 // z = s o acc32; rz' = (s o r).acc32 (the bf16 s o r the GEMM consumed); beta = first ? 0 : rz'/rz; p = z + beta p -> (p_hi, p_lo)
-int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, cudaStream_t s);
+// zb16: acc32 holds the preconditioner product as bf16 rows (tc_gemm out_bf16) -- only when ir_dir_takes_bf16(T)
+bool ir_dir_takes_bf16(int T);
+int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, int zb16, cudaStream_t s);
 // q = acc32 + lam o p; alpha = rz / p.q; d += alpha p (d = alpha p when `first`); r -= alpha q; rsb = bf16(s o r)
 int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, double shift, double c,
               cudaStream_t s);

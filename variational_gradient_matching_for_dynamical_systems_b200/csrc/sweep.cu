@@ -653,12 +653,13 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
         TcGemmArgs tg;
         memset(&tg, 0, sizeof(tg));
         tg.n_rows = n; tg.n_rows_dev = k.n_act; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = ib.acc32; tg.ldo = ld;
-        TcGemmArgs tp = tg;                                 // z' = (s o r) G^T
-        tp.A0 = ib.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G;
+        TcGemmArgs tp = tg;                                 // z' = (s o r) G^T, stored as bf16 when ir_dir can read that
+        const int zb16 = ir_dir_takes_bf16(T) ? 1 : 0;      // (no effect on the convergence: profiles/solver_study.md)
+        tp.A0 = ib.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G; tp.out_bf16 = zb16;
         TcGemmArgs to = tg;                                 // q' = p M^T (bf16 split)
         to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
         VGM_TRY(tc_gemm(tp, st));
-        VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 1, st));
+        VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 1, zb16, st));
         swap_pq();
         for (int it = 0; it < inner; ++it) {
           const int last = (it == inner - 1) ? 1 : 0;
@@ -667,7 +668,7 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
           VGM_TRY(ir_update(ib, n, k.n_act, T, ld, last, it == 0 ? 1 : 0, ops->G_shift, ops->precond_c, st));
           if (last) break;
           VGM_TRY(tc_gemm(tp, st));
-          VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 0, st));
+          VGM_TRY(ir_dir(ib, n, k.n_act, T, ld, 0, zb16, st));
           swap_pq();
         }
         return ir_finish(ib, cb.P, X, slot_state, k.act, n, k.n_act, T, ld, st);

@@ -296,6 +296,38 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
       // memory sees whole 128-byte lines; rows >= n_rows and columns >= M are clipped by the tensor map.
       const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16);
       unsigned char* my_stage = out_stage + (warp - 2) * 2 * TC_OUT_TILE_BYTES;
+      if (a.out_bf16) {
+        // bf16 output: two 32-column TMEM loads make one 64-column (128-byte) row chunk, same swizzle and TMA store
+#pragma unroll 1
+        for (int c = 0; c < TC_BN; c += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr + c, v0);
+          tmem_ld32(taddr + c + 32, v1);
+          const int m0 = ct * TC_BN + c;
+          if (m0 >= a.M) continue;                          // uniform
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          unsigned char* sb = my_stage + epi_buf * TC_OUT_TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t* src = (i < 4) ? (v0 + 8 * i) : (v1 + 8 * (i - 4));
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(src[2 * e]), __uint_as_float(src[2 * e + 1]));
+              w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(sb + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&maps.out, sb, m0, rt * TC_BM + q * 32);
+          epi_buf ^= 1;
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < TC_BN; c += 32) {
         uint32_t v[32];
@@ -456,13 +488,19 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
     VGM_TRY(make_bf16_map(&maps.a1, args.A1, args.n_rows, args.K, args.lda, TC_BM));
     VGM_TRY(make_bf16_map(&maps.b1, args.B1, args.M, args.K, args.ldb, TC_BN));
   }
-  VGM_TRY(make_map(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, args.out, args.n_rows, args.M, args.ldo, 32, 32));
+  if (args.out_bf16) {
+    VGM_REQUIRE((args.ldo % 8) == 0, "bf16 output rows must be 16-byte aligned");
+    VGM_TRY(make_map(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, args.out, args.n_rows, args.M, args.ldo, 64, 32));
+  } else {
+    VGM_TRY(make_map(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, args.out, args.n_rows, args.M, args.ldo, 32, 32));
+  }
   // executed MMA flops (band) and compulsory HBM bytes (A parts once, FP32 output once)
   double ksum = 0.0;
   for (int m0 = 0; m0 < args.M; m0 += TC_BN)
     ksum += args.band > 0 ? (double)(min(args.K, m0 + TC_BN + args.band) - max(0, m0 - args.band)) : (double)args.K;
   const double flops = 2.0 * args.n_rows * TC_BN * ksum * (split ? 3.0 : 1.0);
-  const double bytes = (double)args.n_rows * args.K * 2.0 * (split ? 2.0 : 1.0) + (double)args.n_rows * args.M * 4.0;
+  const double bytes = (double)args.n_rows * args.K * 2.0 * (split ? 2.0 : 1.0) +
+                       (double)args.n_rows * args.M * (args.out_bf16 ? 2.0 : 4.0);
   ProfScope prof(PROF_TCGEMM, flops, bytes, s);
   if (tc_bres_ok(largs, n_sm))
     return split ? tc_launch<true, true>(maps, largs, n_sm, s) : tc_launch<false, true>(maps, largs, n_sm, s);
@@ -491,6 +529,17 @@ extern "C" int vgm_tc_gemm_bf16(const void* A0, const void* A1, int n_rows, int 
   memset(&a, 0, sizeof(a));
   a.n_rows = n_rows; a.M = M; a.K = K; a.band = band;
   a.A0 = A0; a.A1 = A1; a.lda = lda; a.B0 = B0; a.B1 = B1; a.ldb = ldb; a.out = out; a.ldo = ldo;
+  return vgm::tc_gemm(a, (cudaStream_t)stream);
+}
+
+// Same product with the accumulators rounded to bf16 on the way out (out: [n_rows][ldo] bf16).
+extern "C" int vgm_tc_gemm_bf16_out(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1,
+                                    int M, int K, int ldb, int band, void* out_bf16, int ldo, vgm_stream_t stream) {
+  vgm::TcGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_rows = n_rows; a.M = M; a.K = K; a.band = band;
+  a.A0 = A0; a.A1 = A1; a.lda = lda; a.B0 = B0; a.B1 = B1; a.ldb = ldb; a.out = (float*)out_bf16; a.ldo = ldo;
+  a.out_bf16 = 1;
   return vgm::tc_gemm(a, (cudaStream_t)stream);
 }
 

@@ -17,8 +17,9 @@ struct TcGemmArgs {
   const void* B0;           // [M][ldb] bf16
   const void* B1;           // optional low part of B (split)
   int ldb;
-  float* out;               // [n_rows][ldo] fp32
-  int ldo;
+  float* out;               // [n_rows][ldo] fp32 -- or, with out_bf16, [n_rows][ldo] bf16 stored at the same address
+  int ldo;                  // leading dimension of out in ELEMENTS of its type
+  int out_bf16;             // 1: round the accumulators to bf16 on the way out (half the output bytes)
 };
 
 int tc_gemm(const TcGemmArgs& args, cudaStream_t s);
