@@ -284,6 +284,13 @@ int vgm_tc_gemm_bf16(const void* A0, const void* A1, int n_rows, int lda, const 
  * 16-byte pieces: columns M .. round_up(M, 8) - 1 of a row are overwritten with zeros when M is not a multiple of 8. */
 int vgm_tc_gemm_bf16_out(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1, int M, int K,
                          int ldb, int band, void* out_bf16, int ldo, vgm_stream_t stream);
+/* ... and, from the same epilogue, the per-row partial dots of the ROUNDED output with a bf16 weight matrix
+ * W [n_rows][ldw]:  dots[j][ct] = sum over the 128 columns m of column tile ct of bf16(out[j][m]) * W[j][m],
+ * ct < ceil(M / 128) <= ld_dots; M % 8 == 0.  The solver gets r.z of the preconditioned CG this way (W = the A operand
+ * s o r, an L2 hit), so the direction update that follows is a single streaming pass. */
+int vgm_tc_gemm_bf16_out_dots(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1, int M,
+                              int K, int ldb, int band, void* out_bf16, int ldo, const void* W, int ldw, float* dots,
+                              int ld_dots, vgm_stream_t stream);
 
 typedef struct {
   double tol;        /* relative residual ||r|| <= tol ||rhs|| per state (default 1e-13)                     */

@@ -183,6 +183,23 @@ def test_tcgen05_gemm_matches_fp32_reference(pkg, n, T, band, split):
     assert bool((out16[:, (T + 7) // 8 * 8:] == 512.0).all()), "row padding was written"
     assert T % 8 != 0 or bool((out16[:, T:] == 512.0).all())
     assert torch.equal(out16[:, :T], out[:, :T].to(torch.bfloat16))
+    if T % 8 == 0:
+        # ... and the per-row, per-128-column-tile dots of the ROUNDED output with a bf16 weight row, from the same
+        # epilogue (the solver's r.z): fp32 accumulation of 128 products per tile
+        tiles = (T + 127) // 128
+        W = padded(torch.randn((n, T), generator=gen, dtype=torch.float32, device="cuda").to(torch.bfloat16), n)
+        out16b = torch.full((n, ld), 512.0, dtype=torch.bfloat16, device="cuda")
+        dots = torch.full((n, tiles + 1), 777.0, dtype=torch.float32, device="cuda")
+        _lib.check(lib.vgm_tc_gemm_bf16_out_dots(a0.data_ptr(), a1.data_ptr() if split else None, n, ld, b0.data_ptr(),
+                                                 b1.data_ptr() if split else None, T, T, ld, band, out16b.data_ptr(), ld,
+                                                 W.data_ptr(), ld, dots.data_ptr(), tiles + 1, None))
+        torch.cuda.synchronize()
+        assert torch.equal(out16b, out16), "the dots must not change the product"
+        assert bool((dots[:, tiles] == 777.0).all()), "dot padding was written"
+        prod = out16[:, :T].double() * W[:, :T].double()
+        ref_d = torch.stack([prod[:, 128 * c:128 * (c + 1)].sum(dim=1) for c in range(tiles)], dim=1)
+        mag = torch.stack([prod[:, 128 * c:128 * (c + 1)].abs().sum(dim=1) for c in range(tiles)], dim=1)
+        assert float(((dots[:, :tiles].double() - ref_d).abs() / (mag + 1e-30)).max()) < 1e-5
 
 
 def test_mixed_precision_solver_matches_fp64_pcg_and_oracle(pkg):

@@ -105,6 +105,8 @@ SIGNATURES = {
                                    C.c_int, C.c_void_p]),
     "vgm_tc_gemm_bf16_out": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp,
                                        C.c_int, C.c_void_p]),
+    "vgm_tc_gemm_bf16_out_dots": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp,
+                                            C.c_int, c_dp, C.c_int, c_dp, C.c_int, C.c_void_p]),
     "vgm_transpose": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vgm_gm_operators_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vgm_gm_operators": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_size_t,

@@ -6,7 +6,7 @@
 
 namespace vgm {
 
-constexpr int DENSE_MAX_T = 160;   // packed lower triangle of T + 1 rows in shared memory (104 KB at 160: two CTAs per SM)
+constexpr int DENSE_MAX_T = 160;   // lower block triangle + right-hand side block row in shared memory (119 KB at 160)
 
 struct DenseSolveArgs {
   const double* M;           // [T][ld] shared (c I - D)^T (c I - D) when R_uu is the constant c, else null and:

@@ -20,7 +20,8 @@ size_t ir_ws_bytes(int n, int ld) {
   const size_t f32 = align_up((size_t)n * ld * sizeof(float), 256);
   const size_t b16 = align_up((size_t)n * ld * sizeof(__nv_bfloat16), 256);
   const size_t vec = align_up((size_t)n * sizeof(double), 256);
-  return 4 * f32 + 6 * b16 + 2 * vec;
+  const size_t part = align_up((size_t)n * ((ld + 127) / 128) * sizeof(float), 256);
+  return 4 * f32 + 6 * b16 + 2 * vec + part;
 }
 
 void ir_carve(char*& p, int n, int ld, IrBuf& b) {
@@ -39,6 +40,8 @@ void ir_carve(char*& p, int n, int ld, IrBuf& b) {
   b.s16 = (__nv_bfloat16*)p; p += b16;
   b.sigma = (double*)p; p += vec;
   b.rz = (double*)p; p += vec;
+  b.rz_tiles = (ld + 127) / 128;
+  b.rz_part = (float*)p; p += align_up((size_t)n * b.rz_tiles * sizeof(float), 256);
 }
 
 // ---- 4-element vector helpers (rows are 16-byte aligned: ld % 8 == 0) --------------------------------
@@ -250,6 +253,44 @@ __global__ void __launch_bounds__(IR_THREADS, MINB) ir_dir_warp_kernel(IrBuf b, 
   pdl_trigger();
 }
 
+// The same update when the preconditioner GEMM's epilogue has already left (s o r).z' as per-tile partial dots: beta is
+// known after eight loads and a warp sum, so the row is streamed once (z' 2, s 2, p 4 in; p 4 out: 12 B per element
+// instead of 14) and nothing has to wait in registers for a row-wide reduction.
+template <int MINB>
+__global__ void __launch_bounds__(IR_THREADS, MINB) ir_dir_stream_kernel(IrBuf b, const int* __restrict__ n_dev, int n, int T,
+                                                                         int ld, int first) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (IR_THREADS / 32) + (threadIdx.x >> 5);
+  const int nn = n_dev ? min(*n_dev, n) : n;
+  if (j >= nn) return;
+  const size_t o = (size_t)j * ld;
+  const int tiles = (T + 127) >> 7;
+  const double rz_new = warp_sum(lane < tiles ? (double)b.rz_part[(size_t)j * b.rz_tiles + lane] : 0.0);
+  const double rz_old = first ? 0.0 : b.rz[j];
+  const float beta = (first || !(rz_old > 0.0)) ? 0.f : (float)(rz_new / rz_old);
+  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(b.acc32);
+#pragma unroll
+  for (int g = 0; g < IR_WG; ++g) {
+    const int i = 8 * (lane + 32 * g);
+    if (i < T) {                                                // T % 8 == 0: whole groups only
+      const f8 av = ld_bf8(zb + o + i);
+      const f8 sv = ld_bf8(b.s16 + o + i);
+      float4 p0 = mul4(sv.a, av.a), p1 = mul4(sv.b, av.b);
+      if (!first) {
+        const f8 h = ld_bf8(b.p_hi + o + i), l = ld_bf8(b.p_lo + o + i);
+        p0 = axpy4(beta, add4(h.a, l.a), p0);
+        p1 = axpy4(beta, add4(h.b, l.b), p1);
+      }
+      const float4 h0 = bfr4(p0), h1 = bfr4(p1);
+      st_bf8(b.q_hi + o + i, h0, h1);
+      st_bf8(b.q_lo + o + i, sub4(p0, h0), sub4(p1, h1));
+    }
+  }
+  if (lane == 0) b.rz[j] = rz_new;
+  pdl_trigger();
+}
+
 template <bool REG>
 __global__ void __launch_bounds__(IR_THREADS) ir_update_kernel(IrBuf b, const int* __restrict__ n_dev, int T, int ld,
                                                                int last, int first, float sc_num, float sc_c) {
@@ -348,9 +389,22 @@ bool ir_dir_takes_bf16(int T) {
   return !off && ir_dir_variant() != 1 && T <= 8 * 32 * IR_WG && (T % 8) == 0;
 }
 
+// VGM_NO_GEMM_DOTS=1: ir_dir computes (s o r).z' itself (one more 2-byte read per element and a two-phase kernel)
+bool ir_dir_takes_dots() {
+  static const bool off = getenv("VGM_NO_GEMM_DOTS") != nullptr;
+  return !off;
+}
+
 int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, int zb16, cudaStream_t s) {
   if (n <= 0) return VGM_OK;
   VGM_REQUIRE(!zb16 || ir_dir_takes_bf16(T), "ir_dir: bf16 accumulators need the warp-per-row kernel");
+  if (zb16 == 2) {
+    // reads z' 2, s16 2, (p_hi, p_lo 4); writes p_hi, p_lo 4
+    ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * (first ? 8.0 : 12.0), s);
+    const dim3 grid(ceil_div(n, IR_THREADS / 32));
+    VGM_CUDA_OK(launch_pdl(ir_dir_stream_kernel<4>, grid, dim3(IR_THREADS), 0, s, b, n_dev, n, T, ld, first));
+    return VGM_OK;
+  }
   // reads acc 4 (2 as bf16), s16 2, rsb 2, (p_hi, p_lo 4); writes p_hi, p_lo 4
   ProfScope prof(PROF_IR_DIR, 0.0, (double)n * T * ((first ? 12.0 : 16.0) - (zb16 ? 2.0 : 0.0)), s);
   // VGM_IR_DIR_VARIANT=1: one CTA per row with the row in registers (like ir_update) instead of one warp per row

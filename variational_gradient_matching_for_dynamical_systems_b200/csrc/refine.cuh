@@ -13,6 +13,8 @@ struct IrBuf {
                                           // reading and rewriting the same bf16 lines in one kernel cost it 12 %
   __nv_bfloat16 *rsb, *s16;               // [n][ld] bf16(s o r) (A operand of the preconditioner GEMM), scaling s
   double *sigma, *rz;                     // [n] residual norm each row was scaled by; r.z
+  float* rz_part;                         // [n][rz_tiles] partial dots (s o r).z' per 128-column tile, written by the
+  int rz_tiles;                           // preconditioner GEMM's epilogue (tc_gemm dot_out); rz_tiles = ceil(ld / 128)
 };
 
 size_t ir_ws_bytes(int n, int ld);
@@ -26,7 +28,9 @@ int ir_inner_init(const IrBuf& b, const double* R, const double* Lambda, const d
                   const int* n_dev, int T, int ld, double shift, double c, cudaStream_t s);
 // z = s o acc32; rz' = (s o r).acc32 (the bf16 s o r the GEMM consumed); beta = first ? 0 : rz'/rz; p = z + beta p -> (p_hi, p_lo)
 // zb16: acc32 holds the preconditioner product as bf16 rows (tc_gemm out_bf16) -- only when ir_dir_takes_bf16(T)
+// zb16 == 2: rz' additionally comes from the GEMM epilogue's partial dots (b.rz_part), so the row is streamed once
 bool ir_dir_takes_bf16(int T);
+bool ir_dir_takes_dots();
 int ir_dir(const IrBuf& b, int n, const int* n_dev, int T, int ld, int first, int zb16, cudaStream_t s);
 // q = acc32 + lam o p; alpha = rz / p.q; d += alpha p (d = alpha p when `first`); r -= alpha q; rsb = bf16(s o r)
 int ir_update(const IrBuf& b, int n, const int* n_dev, int T, int ld, int last, int first, double shift, double c,

@@ -497,7 +497,7 @@ static IrBuf ir_view(const IrBuf& b, int row0, int ld) {
   const size_t o = (size_t)row0 * ld;
   v.r32 += o; v.d32 += o; v.acc32 += o; v.lam32 += o;
   v.p_hi += o; v.p_lo += o; v.q_hi += o; v.q_lo += o; v.rsb += o; v.s16 += o;
-  v.sigma += row0; v.rz += row0;
+  v.sigma += row0; v.rz += row0; v.rz_part += (size_t)row0 * b.rz_tiles;
   return v;
 }
 
@@ -654,8 +654,10 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
         memset(&tg, 0, sizeof(tg));
         tg.n_rows = n; tg.n_rows_dev = k.n_act; tg.M = T; tg.K = T; tg.lda = ld; tg.ldb = ld; tg.out = ib.acc32; tg.ldo = ld;
         TcGemmArgs tp = tg;                                 // z' = (s o r) G^T, stored as bf16 when ir_dir can read that
-        const int zb16 = ir_dir_takes_bf16(T) ? 1 : 0;      // (no effect on the convergence: profiles/solver_study.md)
-        tp.A0 = ib.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G; tp.out_bf16 = zb16;
+        // (no effect on the convergence: profiles/solver_study.md); 2: the GEMM epilogue also leaves (s o r).z' per tile
+        const int zb16 = ir_dir_takes_bf16(T) ? (ir_dir_takes_dots() ? 2 : 1) : 0;
+        tp.A0 = ib.rsb; tp.B0 = ops->G_bf16; tp.band = ops->band_G; tp.out_bf16 = zb16 ? 1 : 0;
+        if (zb16 == 2) { tp.dot_w = ib.rsb; tp.dot_ldw = ld; tp.dot_out = ib.rz_part; tp.dot_ld = ib.rz_tiles; }
         TcGemmArgs to = tg;                                 // q' = p M^T (bf16 split)
         to.B0 = M_hi; to.B1 = M_lo; to.band = ops->band_M_lp;
         VGM_TRY(tc_gemm(tp, st));

@@ -288,6 +288,19 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
       const int rt = BRES ? u : u / col_tiles, ct = BRES ? ct_fixed : u % col_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      // partial dots: the 128 weights of this thread's row are fetched BEFORE the accumulator is waited for, so the
+      // latency hides behind the MMAs of the tile.  (Staging them through shared memory by TMA instead of these
+      // row-per-thread reads changed nothing: what the dots cost the GEMM, +15 us on 43 us, is the second pass of the
+      // weight rows through L2.)
+      const int row = rt * TC_BM + q * 32 + lane;
+      const bool dot = a.out_bf16 && a.dot_out != nullptr && row < n_rows;
+      uint4 wv[16];
+      if (dot) {
+        const __nv_bfloat16* wrow = reinterpret_cast<const __nv_bfloat16*>(a.dot_w) + (size_t)row * a.dot_ldw + ct * TC_BN;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          wv[i] = (ct * TC_BN + 8 * i < a.M) ? __ldg(reinterpret_cast<const uint4*>(wrow + 8 * i)) : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       // This thread's TMEM lane is row rt*128 + q*32 + lane.  A warp moves its 32 x 32 chunk through shared
@@ -298,8 +311,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
       unsigned char* my_stage = out_stage + (warp - 2) * 2 * TC_OUT_TILE_BYTES;
       if (a.out_bf16) {
         // bf16 output: two 32-column TMEM loads make one 64-column (128-byte) row chunk, same swizzle and TMA store
-#pragma unroll 1
-        for (int c = 0; c < TC_BN; c += 64) {
+        float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};   // eight independent chains
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 64 * cc;
           uint32_t v0[32], v1[32];
           tmem_ld32(taddr + c, v0);
           tmem_ld32(taddr + c + 32, v1);
@@ -317,6 +332,15 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
               const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(src[2 * e]), __uint_as_float(src[2 * e + 1]));
               w[e] = *reinterpret_cast<const uint32_t*>(&h);
             }
+            if (dot) {
+              const uint4 wq = wv[8 * cc + i];
+              const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pa[e] = fmaf(__uint_as_float(w[e] << 16), __uint_as_float(ww[e] << 16), pa[e]);
+                pb[e] = fmaf(__uint_as_float(w[e] & 0xffff0000u), __uint_as_float(ww[e] & 0xffff0000u), pb[e]);
+              }
+            }
             *reinterpret_cast<uint4*>(sb + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -324,6 +348,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
           if (lane == 0) tma_store_2d(&maps.out, sb, m0, rt * TC_BM + q * 32);
           epi_buf ^= 1;
         }
+        if (dot) a.dot_out[(size_t)row * a.dot_ld + ct] = ((pa[0] + pb[0]) + (pa[1] + pb[1])) + ((pa[2] + pb[2]) + (pa[3] + pb[3]));
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
         continue;
@@ -490,6 +515,14 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
   }
   if (args.out_bf16) {
     VGM_REQUIRE((args.ldo % 8) == 0, "bf16 output rows must be 16-byte aligned");
+    if (args.dot_out)
+      VGM_REQUIRE(args.dot_w && (args.M % 8) == 0 && (args.dot_ldw % 8) == 0 && ((uintptr_t)args.dot_w % 16) == 0 &&
+                      args.dot_ld >= (args.M + TC_BN - 1) / TC_BN,
+                  "tc_gemm partial dots: M % 8 == 0, 16-byte aligned bf16 weight rows, dot_ld >= ceil(M / 128)");
+  } else {
+    VGM_REQUIRE(!args.dot_out, "tc_gemm partial dots need the bf16 output");
+  }
+  if (args.out_bf16) {
     VGM_TRY(make_map(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, args.out, args.n_rows, args.M, args.ldo, 64, 32));
   } else {
     VGM_TRY(make_map(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, args.out, args.n_rows, args.M, args.ldo, 32, 32));
@@ -561,4 +594,18 @@ extern "C" int vgm_split_bf16(const double* in, void* out_bf16x2, int rows, int 
   vgm::f64_split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16x2, n);
   VGM_LAUNCH_OK();
   return VGM_OK;
+}
+
+// vgm_tc_gemm_bf16_out plus the per-row partial dots of the rounded output with a bf16 weight matrix W [n_rows][ldw]:
+// dots[j][ct] = sum_{m in column tile ct} bf16(out[j][m]) W[j][m], ct < ceil(M / 128) <= ld_dots  (M % 8 == 0).
+extern "C" int vgm_tc_gemm_bf16_out_dots(const void* A0, const void* A1, int n_rows, int lda, const void* B0, const void* B1,
+                                         int M, int K, int ldb, int band, void* out_bf16, int ldo, const void* W, int ldw,
+                                         float* dots, int ld_dots, vgm_stream_t stream) {
+  vgm::TcGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_rows = n_rows; a.M = M; a.K = K; a.band = band;
+  a.A0 = A0; a.A1 = A1; a.lda = lda; a.B0 = B0; a.B1 = B1; a.ldb = ldb; a.out = (float*)out_bf16; a.ldo = ldo;
+  a.out_bf16 = 1;
+  a.dot_w = W; a.dot_ldw = ldw; a.dot_out = dots; a.dot_ld = ld_dots;
+  return vgm::tc_gemm(a, (cudaStream_t)stream);
 }

@@ -20,6 +20,13 @@ struct TcGemmArgs {
   float* out;               // [n_rows][ldo] fp32 -- or, with out_bf16, [n_rows][ldo] bf16 stored at the same address
   int ldo;                  // leading dimension of out in ELEMENTS of its type
   int out_bf16;             // 1: round the accumulators to bf16 on the way out (half the output bytes)
+  // optional, with out_bf16 and M % 8 == 0: per-row partial dots of the ROUNDED output with a bf16 weight row,
+  // dot_out[j][ct] = sum over the 128 columns of column tile ct of bf16(out[j][m]) * dot_w[j][m]   (the epilogue thread
+  // that owns row j of a tile holds those 128 accumulators anyway; the weight row is an L2 hit when it is the A operand)
+  const void* dot_w;        // [n_rows][dot_ldw] bf16
+  int dot_ldw;
+  float* dot_out;           // [n_rows][dot_ld], dot_ld >= ceil(M / 128)
+  int dot_ld;
 };
 
 int tc_gemm(const TcGemmArgs& args, cudaStream_t s);
