@@ -115,7 +115,9 @@ int vgm_dgemm_set_variant(int variant); /* tile configuration of the large-N GEM
 int vgm_dgemm_dot_tiles(int M, int N); /* number of column tiles written per row of dot_out */
 /* Smallest b such that |B[i][j]| <= rel_threshold * max|B| whenever |i - j| > b (synchronises the stream).
  * With rel_threshold = 2^-64 the dropped part of any product is below half an ulp of the kept part's
- * normwise rounding error, i.e. the banded GEMM is FP64-exact in the backward sense. */
+ * normwise rounding error, i.e. the banded GEMM is FP64-exact in the backward sense; the engine uses 2^-55, where
+ * the dropped part of a row of geometrically decaying operators stays below two units of round-off of
+ * max|B| max|x| (less than the rounding error of the kept part's accumulation). */
 int vgm_band_halfwidth(const double* B, int rows, int cols, int ld, double rel_threshold, int* band_host,
                        vgm_stream_t stream);
 /* Per-launch CUDA-event timing of the kernel families (used by bench.py for the roofline figures):
@@ -259,7 +261,7 @@ typedef struct {
                            corrections by FP32 PCG whose operator products run on the tcgen05 tensor cores  */
   double G_shift;       /* the shift G was built with                                                          */
   double precond_c;     /* > 0: the preconditioner is S G S with S = diag sqrt((G_shift + c) / (Lambda + c))    */
-  int band_D, band_M;   /* half band widths of D (and D^T) and M at the FP64-exact threshold 2^-64
+  int band_D, band_M;   /* half band widths of D (and D^T) and M at the engine's FP64 threshold 2^-55
                            (vgm_band_halfwidth); <= 0: dense                                                  */
   int band_M_lp, band_G; /* half band widths used on the low-precision side: M at ~2^-20 (the bf16-split product
                            resolves 2^-16), G at ~2^-7 (a preconditioner only has to stay SPD); <= 0: dense   */

@@ -6,7 +6,7 @@
 // With both operands split into bf16 (hi, lo) pairs the three leading products give ~2^-16 relative
 // accuracy with FP32 accumulation -- enough for the correction solves of iterative refinement, whose
 // residuals stay in FP64 on the DMMA pipe (sweep.cu).  The operators of the hot path are numerically
-// banded (|B[m][k]| < 2^-64 max|B| beyond the band), so a column tile only visits the k-blocks inside
+// banded (negligible entries beyond the band), so a column tile only visits the k-blocks inside
 // [m0 - band, m0 + BN + band).
 // One persistent CTA per SM, warp-specialised:
 //   warp 0     TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier ring; one stage = the A and B
