@@ -668,13 +668,13 @@ def native_arm(args):
                "; FP64: cuBLAS DGEMM 8192^3 measured on this pool (profiles/fp64_peak.json)"
     names = {"dgemm": "vgm::dgemm_nt_kernel (FP64 DMMA, banded)",
              "tcgemm": "vgm::tc_gemm_kernel<split|single> (tcgen05 bf16, banded, operator-resident)",
-             "ir_update": "vgm::ir_update_kernel", "ir_dir": "vgm::ir_dir_warp_kernel",
+             "ir_update": "vgm::ir_update_kernel", "ir_dir": "vgm::ir_dir_stream_kernel (beta from the GEMM epilogue's partial dots)",
              "vec_other": "vgm::ir_inner_init/ir_finish/ir_prep/cg_gather_x", "assemble": "state_assemble + param_stats"}
     # DRAM bytes per launch: NOT measured in this run -- read from the committed `ncu --set full` capture of the same
     # kernels at the same shape (profiles/r02_ncu_traffic.json, made by scripts/ncu_summarise.py from
     # scripts/ncu_targets.py at K=100000, T=1000; table in profiles/r02_ncu_summary.md)
     fam_kernel = {"dgemm": "void dgemm_nt_kernel", "tcgemm": "void tc_gemm_kernel", "ir_update": "void ir_update_kernel",
-                  "ir_dir": "ir_dir_warp_kernel", "assemble": "vgm_lorenz96_state_assemble", "vec_other": "ir_inner_init_kernel"}
+                  "ir_dir": "void ir_dir_stream_kernel", "assemble": "vgm_lorenz96_state_assemble", "vec_other": "ir_inner_init_kernel"}
     try:
         with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             cap = json.load(f)
