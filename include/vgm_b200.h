@@ -39,7 +39,8 @@ enum {
   VGM_ECUDA = -2,    /* CUDA runtime error                                      */
   VGM_ENOTCONV = -3, /* iterative solve hit max_iter before reaching tolerance  */
   VGM_ENOTSPD = -4,  /* Cholesky pivot <= 0                                     */
-  VGM_EDRIVER = -5   /* CUDA driver API / module loading failure                */
+  VGM_EDRIVER = -5,  /* CUDA driver API / module loading failure                */
+  VGM_ENCCL = -6     /* NCCL not loadable, or an NCCL call failed (vgm_comm_*)  */
 };
 
 const char* vgm_last_error(void);
@@ -422,6 +423,40 @@ int vgm_iteration_host(const vgm_program* prog, const vgm_model_tables* model, c
  * (state-major, leading dimension ld).  n_sub <= 8; scratch holds 2 K doubles.  One launch per grid interval. */
 int vgm_lorenz96_rk4(const double* x0, int K, double alpha, double h, int n_sub, int n_spinup, int n_grid, double* X,
                      int ld, double* scratch, vgm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU exchange steps, one process per GPU.  The path has two exchanges per iteration and these
+ * are thin NCCL wrappers for exactly those; everything else a rank does is the single-GPU entry points above on its
+ * own block of states (or trajectories).  NCCL is resolved at run time (dlopen of the libnccl.so.2 already in the
+ * process, else from the loader path): the library loads without it and these functions then return VGM_ENCCL.
+ *
+ *   vgm_comm_unique_id       rank 0 creates the 128-byte id and hands it to the other ranks out of band (file, MPI,
+ *                            torch.distributed ... -- the same bytes an `ncclUniqueId` holds)
+ *   vgm_comm_init            collective: every rank calls it with its rank on its current device (ncclCommInitRank)
+ *   vgm_comm_allreduce_stats in-place sum over ranks of the parameter statistics [m | S] (p + p^2 doubles) that
+ *                            vgm_param_stats wrote for this rank's ODE rows: the sum over k of
+ *                            proxies_for_ode_parameters_and_states.py:64-79 (`local_mean += ...`, `local_scaling += ...`)
+ *                            split over ranks; vgm_param_solve then runs redundantly on every rank
+ *   vgm_comm_halo_exchange   snapshot halo of the state sweep (proxies...py:191, one copy of the states per sweep; the
+ *                            coefficients of state u read its coupled neighbours, u-3 .. u+3 for Lorenz96): rank r
+ *                            publishes rows pub_rows[0 .. n_pub_mine) of its X (n_pub = the maximum count over ranks,
+ *                            identical on every rank), ONE all-gather, then X[halo_rows[i]] = gathered[halo_src[i]]
+ *                            for i < n_halo with halo_src = owner_rank * n_pub + position in the owner's pub_rows.
+ *                            pub_rows / halo_rows / halo_src are DEVICE int arrays; ws holds
+ *                            vgm_comm_halo_ws_bytes(world, n_pub, ld) bytes.  n_pub == 0 (trajectory batches): no-op.
+ * All calls enqueue on `stream` and return; ranks must issue them in the same order. */
+#define VGM_COMM_ID_BYTES 128
+typedef struct vgm_comm vgm_comm;
+int vgm_comm_nccl_version(int* version_host);
+int vgm_comm_unique_id(void* id_host);
+int vgm_comm_init(const void* id_host, int rank, int world, vgm_comm** comm);
+int vgm_comm_free(vgm_comm* comm);
+int vgm_comm_rank(const vgm_comm* comm, int* rank_host, int* world_host);
+int vgm_comm_allreduce_stats(vgm_comm* comm, double* stats, int n, vgm_stream_t stream);
+size_t vgm_comm_halo_ws_bytes(int world, int n_pub, int ld);
+int vgm_comm_halo_exchange(vgm_comm* comm, double* X, int ld, const int* pub_rows, int n_pub_mine, int n_pub,
+                           const int* halo_rows, const int* halo_src, int n_halo, void* ws, size_t ws_bytes,
+                           vgm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -43,15 +43,19 @@ def main():
         single.set_states_state_major(X0)
         multi = DistributedVGMEngine(model, D, None, hidden=hidden)
         multi.set_states_state_major(X0)
-        errs = []
+        # the same engine with both exchanges through the library's own C-ABI wrappers (vgm_comm_*)
+        native = DistributedVGMEngine(model, D, None, hidden=hidden, comm="native")
+        native.set_states_state_major(X0)
+        errs, errs_native = [], []
         for it in range(2):
             single.iteration()
             multi.iteration()
+            native.iteration()
             Xs = single.X[:, :T]
-            Xm = multi.gather_states()
-            ex = ((Xs - Xm).abs().max() / Xs.abs().max()).item()
-            et = abs(single.get_theta()[0] - multi.get_theta()[0]) / abs(single.get_theta()[0])
-            errs.append((ex, et))
+            th = single.get_theta()[0]
+            for eng, out in ((multi, errs), (native, errs_native)):
+                Xm = eng.gather_states()
+                out.append((((Xs - Xm).abs().max() / Xs.abs().max()).item(), abs(th - eng.get_theta()[0]) / abs(th)))
         # pooled 'minimizer' loss / gradient: sum over the ranks' ODE rows == single-GPU value
         single.compute_DX()
         multi.halo(multi.engine.X)
@@ -60,9 +64,12 @@ def main():
         lm, gm = multi.param_loss([7.5], alpha=0.3)
         errs.append((0.0, max(abs(ls - lm) / abs(ls), float(np.max(np.abs(gs - gm)) / np.max(np.abs(gs))))))
         res[tag] = {"state_rel_err": max(e[0] for e in errs), "theta_rel_err": max(e[1] for e in errs),
+                    "native_comm_state_rel_err": max(e[0] for e in errs_native),
+                    "native_comm_theta_rel_err": max(e[1] for e in errs_native),
                     "levels": multi.n_levels, "shift": multi.shift, "cross_rank_live": multi.cross_rank_live,
                     "tail_overlap_ranks": int(_sum_int(multi.engine.plan.c.n_early > 0, dev))}
-    ok = all(v["state_rel_err"] < 1e-10 and v["theta_rel_err"] < 1e-11 for v in res.values())
+    ok = all(v["state_rel_err"] < 1e-10 and v["theta_rel_err"] < 1e-11 and v["native_comm_state_rel_err"] < 1e-10
+             and v["native_comm_theta_rel_err"] < 1e-11 for v in res.values())
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

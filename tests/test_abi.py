@@ -62,6 +62,24 @@ def test_no_cpu_fallback_without_gpu():
         VGMEngine(OdeModel.lorenz96(10), np.eye(8))
 
 
+def test_comm_wrappers_resolve_nccl_at_run_time():
+    """vgm_comm_*: NCCL is dlopen'ed on first use (the copy PyTorch already loaded), the id needs no GPU, and a
+    communicator cannot be created without a device (no CPU fallback)."""
+    import torch
+    from variational_gradient_matching_for_dynamical_systems_b200 import _lib
+    lib = _lib.load()
+    ver = ctypes.c_int(0)
+    assert lib.vgm_comm_nccl_version(ctypes.byref(ver)) == _lib.VGM_OK, lib.vgm_last_error()
+    major, minor, patch = torch.cuda.nccl.version()[:3]
+    assert ver.value == major * 10000 + minor * 100 + patch
+    assert lib.vgm_comm_halo_ws_bytes(8, 6, 1024) == 9 * 6 * 1024 * 8
+    if not torch.cuda.is_available():
+        ident = ctypes.create_string_buffer(_lib.COMM_ID_BYTES)
+        comm = ctypes.c_void_p()
+        assert lib.vgm_comm_init(ident.raw, 0, 1, ctypes.byref(comm)) in (_lib.VGM_ECUDA, _lib.VGM_ENCCL)
+        assert not comm.value
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "variational_gradient_matching_for_dynamical_systems_b200")
     for dp, _, files in os.walk(pkg):

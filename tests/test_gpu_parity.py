@@ -963,6 +963,46 @@ def test_two_rank_state_block_partition_matches_single_gpu():
     assert '"ok": true' in out.stdout
 
 
+def test_comm_c_abi_single_rank(pkg):
+    """vgm_comm_* through the C ABI on a one-rank NCCL communicator: the statistics all-reduce is the identity and
+    the halo exchange (pack kernel -> ncclAllGather -> unpack kernel) moves exactly the published rows."""
+    import ctypes as C
+    _, _lib, _ = pkg
+    lib = _lib.load()
+    ver = C.c_int(0)
+    _lib.check(lib.vgm_comm_nccl_version(C.byref(ver)))
+    assert ver.value >= 20000
+    ident = C.create_string_buffer(_lib.COMM_ID_BYTES)
+    _lib.check(lib.vgm_comm_unique_id(ident))
+    comm = C.c_void_p()
+    _lib.check(lib.vgm_comm_init(ident.raw, 0, 1, C.byref(comm)))
+    try:
+        r, w = C.c_int(-1), C.c_int(-1)
+        _lib.check(lib.vgm_comm_rank(comm, C.byref(r), C.byref(w)))
+        assert (r.value, w.value) == (0, 1)
+        dev = torch.device("cuda")
+        stats = torch.arange(1.0, 7.0, dtype=torch.float64, device=dev)
+        _lib.check(lib.vgm_comm_allreduce_stats(comm, stats.data_ptr(), stats.numel(), _lib.stream_ptr()))
+        assert torch.equal(stats.cpu(), torch.arange(1.0, 7.0, dtype=torch.float64))
+        ld, n_rows, n_pub = 1024, 12, 3
+        X = torch.randn(n_rows, ld, dtype=torch.float64, device=dev)
+        X0 = X.clone()
+        pub = torch.tensor([2, 5], dtype=torch.int32, device=dev)          # this rank publishes 2 rows, padded to 3
+        halo_rows = torch.tensor([9, 10, 11], dtype=torch.int32, device=dev)
+        halo_src = torch.tensor([1, 0, 1], dtype=torch.int32, device=dev)  # rank 0 * n_pub + position
+        ws = torch.empty(lib.vgm_comm_halo_ws_bytes(1, n_pub, ld), dtype=torch.uint8, device=dev)
+        _lib.check(lib.vgm_comm_halo_exchange(comm, X.data_ptr(), ld, pub.data_ptr(), 2, n_pub, halo_rows.data_ptr(),
+                                              halo_src.data_ptr(), 3, ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(X[:9], X0[:9])
+        assert torch.equal(X[9], X0[5]) and torch.equal(X[10], X0[2]) and torch.equal(X[11], X0[5])
+        # a workspace that is too small is refused before anything is enqueued
+        assert lib.vgm_comm_halo_exchange(comm, X.data_ptr(), ld, pub.data_ptr(), 2, n_pub, halo_rows.data_ptr(),
+                                          halo_src.data_ptr(), 3, ws.data_ptr(), 16, _lib.stream_ptr()) == _lib.VGM_EINVAL
+    finally:
+        _lib.check(lib.vgm_comm_free(comm))
+
+
 def test_dropin_api_call_sequence_matches_reference_golden(pkg, tmp_path):
     """The reference's own call sequence (VGM_for_Lotka_Volterra.ipynb cells 25-41) through the
     drop-in modules, DataFrames in / DataFrames out, against the live reference's output."""

@@ -13,7 +13,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgm_b200.so")
 
-VGM_OK, VGM_EINVAL, VGM_ECUDA, VGM_ENOTCONV, VGM_ENOTSPD, VGM_EDRIVER = 0, -1, -2, -3, -4, -5
+VGM_OK, VGM_EINVAL, VGM_ECUDA, VGM_ENOTCONV, VGM_ENOTSPD, VGM_EDRIVER, VGM_ENCCL = 0, -1, -2, -3, -4, -5, -6
+COMM_ID_BYTES = 128
 KERNEL_RBF, KERNEL_RQ = 0, 1
 (KERNEL_PERIODIC, KERNEL_LOCALLY_PERIODIC, KERNEL_RBF_LIN, KERNEL_SIGMOID, KERNEL_SIGMOID2, KERNEL_EXP_SIN_SQUARED,
  KERNEL_MATERN) = range(2, 9)
@@ -155,6 +156,15 @@ SIGNATURES = {
     "vgm_iteration_host": (C.c_int, [C.c_void_p, _P(ModelTables), _P(SweepPlan), _P(Operators), _P(SolverOpts),
                                      c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_size_t, _P(SweepInfo),
                                      C.c_void_p]),
+    "vgm_comm_nccl_version": (C.c_int, [_P(C.c_int)]),
+    "vgm_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "vgm_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, _P(C.c_void_p)]),
+    "vgm_comm_free": (C.c_int, [C.c_void_p]),
+    "vgm_comm_rank": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_int)]),
+    "vgm_comm_allreduce_stats": (C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_void_p]),
+    "vgm_comm_halo_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "vgm_comm_halo_exchange": (C.c_int, [C.c_void_p, c_dp, C.c_int, c_ip, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_dp,
+                                         C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

@@ -11,6 +11,10 @@ and, in both cases, one all-reduce (sum) of the ODE-parameter sufficient statist
 ``[m | S]`` (p + p^2 doubles) per iteration, after which every rank solves the p x p system
 redundantly.  Every rank executes the *global* dependency levels in the reference's order, so
 the result is the single-GPU result (up to the summation order of the all-reduce).
+
+``comm="native"`` routes both exchanges through the library's own C-ABI wrappers (``vgm_comm_halo_exchange``: pack
+kernel -> ``ncclAllGather`` -> unpack kernel on one stream; ``vgm_comm_allreduce_stats``), i.e. exactly what a
+C / C++ caller without PyTorch would call; ``torch.distributed`` then only carries the 128-byte NCCL id at set-up.
 """
 from __future__ import annotations
 
@@ -18,7 +22,46 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from .codegen import HostPlan, OdeModel, build_host_plan
+
+
+class NativeComm:
+    """A ``vgm_comm`` (include/vgm_b200.h): the library's own NCCL communicator over the ranks of a
+    ``torch.distributed`` group, which is used once, to hand rank 0's 128-byte NCCL id to the others."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        self.lib = _lib.load()                       # torch is imported above: the process's libnccl.so.2 is torch's
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        if self.rank == 0:
+            _lib.check(self.lib.vgm_comm_unique_id(ident))
+        box = [ident.raw if self.rank == 0 else None]
+        src = 0 if group is None else dist.get_global_rank(group, 0)
+        dist.broadcast_object_list(box, src=src, group=group)
+        handle = C.c_void_p()
+        _lib.check(self.lib.vgm_comm_init(box[0], self.rank, self.world, C.byref(handle)))
+        self.handle = handle
+
+    def allreduce_stats(self, stats):
+        """In-place sum over ranks of a contiguous FP64 device tensor, on the current stream."""
+        _lib.check(self.lib.vgm_comm_allreduce_stats(self.handle, stats.data_ptr(), stats.numel(), _lib.stream_ptr()))
+
+    def halo_ws(self, n_pub, ld, device):
+        return torch.empty(max(self.lib.vgm_comm_halo_ws_bytes(self.world, n_pub, ld), 16), dtype=torch.uint8, device=device)
+
+    def halo_exchange(self, X, pub_rows, n_pub, halo_rows, halo_src, ws):
+        _lib.check(self.lib.vgm_comm_halo_exchange(self.handle, X.data_ptr(), X.shape[1], _lib.ptr(pub_rows),
+                                                   0 if pub_rows is None else pub_rows.numel(), n_pub,
+                                                   _lib.ptr(halo_rows), _lib.ptr(halo_src),
+                                                   0 if halo_rows is None else halo_rows.numel(), ws.data_ptr(),
+                                                   ws.numel(), _lib.stream_ptr()))
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.vgm_comm_free(self.handle)
+            self.handle = None
 
 
 def block_bounds(n_items, world, align=1, weights=None):
@@ -215,8 +258,9 @@ class HaloExchange:
     """Refresh of the halo rows of X: every rank contributes the owned rows that any other
     rank reads (padded to a common count) to one all-gather and then picks its halo rows."""
 
-    def __init__(self, loc: Localized, bounds, group=None, shift=0, K=None):
+    def __init__(self, loc: Localized, bounds, group=None, shift=0, K=None, comm=None):
         self.group = group
+        self.comm = comm                                # NativeComm: vgm_comm_halo_exchange instead of torch ops
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         halos = [None] * self.world
@@ -244,6 +288,14 @@ class HaloExchange:
         if self.empty:
             return
         ld = X.shape[1]
+        if self.comm is not None:
+            if self._buf is None or self._buf[0] != ld or self._buf[1].device != X.device:
+                as_i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=X.device) if len(a) else None
+                self._buf = (ld, self.comm.halo_ws(self.n_pub, ld, X.device), as_i32(self.pub_rows_local),
+                             as_i32(self.halo_rows_local), as_i32(self.src_flat))
+            _, ws, pub_idx, halo_idx, src_idx = self._buf
+            self.comm.halo_exchange(X, pub_idx, self.n_pub, halo_idx, src_idx, ws)
+            return
         if self._buf is None or self._buf[0].shape[1] != ld or self._buf[0].device != X.device:
             self._buf = (torch.zeros((self.n_pub, ld), dtype=X.dtype, device=X.device),
                          torch.zeros((self.world * self.n_pub, ld), dtype=X.dtype, device=X.device),
@@ -268,9 +320,13 @@ class DistributedVGMEngine:
     TAIL_LEVEL_COST_STATES = 0
 
     def __init__(self, model: OdeModel, D, A=None, hidden=None, schedule="reference", align=2, group=None,
-                 tail_level_cost_states=None, shift="auto", **kw):
+                 tail_level_cost_states=None, shift="auto", comm="torch", **kw):
         from .engine import LocalProblem, VGMEngine
+        if comm not in ("torch", "native"):
+            raise ValueError("comm must be 'torch' (torch.distributed collectives) or 'native' (vgm_comm_* C ABI)")
         self.group = group
+        self.comm = NativeComm(group) if comm == "native" else None
+        self._side = None
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.model = model
@@ -296,7 +352,7 @@ class DistributedVGMEngine:
         prob = LocalProblem(self.loc.n_rows, self.loc.n_stats_odes, self.loc.ode_class, self.loc.ode_idx,
                             self.loc.ode_state, self.loc.plan, model.p)
         self.engine = VGMEngine(model, D, A, problem=prob, **kw)
-        self.halo = HaloExchange(self.loc, self.bounds, group=group, shift=self.shift, K=model.K)
+        self.halo = HaloExchange(self.loc, self.bounds, group=group, shift=self.shift, K=model.K, comm=self.comm)
         self.n_hidden_global = hp.n_hidden
         self.n_levels = hp.n_levels
 
@@ -355,7 +411,16 @@ class DistributedVGMEngine:
         # With the reference's literal theta in the state update (proxies...py:211) the sweep does not read the new
         # theta: the all-reduce then runs beside the sweep and nobody waits for the slowest rank in mid-iteration.
         late_theta = e.theta_mode == "reference"
-        work = dist.all_reduce(e.stats, op=dist.ReduceOp.SUM, group=self.group, async_op=late_theta)
+        if self.comm is None:
+            work = dist.all_reduce(e.stats, op=dist.ReduceOp.SUM, group=self.group, async_op=late_theta)
+        elif late_theta:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=e.dev)
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                self.comm.allreduce_stats(e.stats)
+        else:
+            self.comm.allreduce_stats(e.stats)
         if not late_theta:
             e.param_solve()
         e.sweep_prepare()
@@ -368,7 +433,10 @@ class DistributedVGMEngine:
                     self.halo(e.X)                       # rows updated by their owners in level lev-1
                 e.sweep_level(lev, allow_unconverged=allow_unconverged)
         if late_theta:
-            work.wait()
+            if self.comm is None:
+                work.wait()
+            else:
+                torch.cuda.current_stream().wait_stream(self._side)
             e.param_solve()
         return e.last_info
 
