@@ -492,7 +492,8 @@ def native_arm(args):
               optimistic_passes=args.optimistic_passes)
     if world > 1:
         from variational_gradient_matching_for_dynamical_systems_b200.distributed import DistributedVGMEngine
-        eng = DistributedVGMEngine(model, ops, None, hidden=hidden, **kw)
+        # VGM_COMM=native: both exchanges through the library's vgm_comm_* entry points instead of torch.distributed
+        eng = DistributedVGMEngine(model, ops, None, hidden=hidden, comm=os.environ.get("VGM_COMM", "torch"), **kw)
         core = eng.engine
         eng.set_states_state_major(X0)
         X0_local = core.X.clone()
@@ -728,6 +729,9 @@ def native_arm(args):
                          (args.tol, "none" if args.no_precondition else "(M+shift I)^-1")),
                         "bands": {"D": core.ops.band_D, "M": core.ops.band_M, "M_bf16": core.ops.band_M_lp,
                                   "G_bf16": core.ops.band_G},
+                        "comm": ("single GPU" if world == 1 else
+                                 "vgm_comm_* (own NCCL communicator)" if os.environ.get("VGM_COMM") == "native"
+                                 else "torch.distributed (NCCL)"),
                         "state_array_mb_per_gpu": n_hidden_local * core.ld * 8 / 1e6,
                         "profiled_ms_per_step": (ms_prof / args.steps) if ms_prof else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "c4": c4, "colour_schedule": colour, "gpu_launches": launches,

@@ -13,6 +13,8 @@
 // (a T x T operator, 8 MB at T=1000) stays L2 resident; the A operand streams from HBM once
 // per column-tile sweep.  Operands are staged through a 4-deep cp.async ring in shared
 // memory with a +4 double row pad (conflict-free 64-bit fragment loads).
+#include <stdlib.h>
+
 #include "vgm_common.cuh"
 #include "vgm_profile.cuh"
 
@@ -28,6 +30,9 @@ struct GemmCfg {
   static constexpr int SMEM = STAGES * (BM + BN) * LDS * (int)sizeof(double);
   static_assert(WM % 16 == 0 && WN % 8 == 0, "warp tile must be a multiple of the MMA tile");
 };
+
+// VGM_NO_RAGGED_BAND=1 (experiments): every MMA tile runs the k range of its whole CTA tile, as before round 2's end
+__device__ int g_no_ragged_dev = 0;
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const vgm_gemm_args a) {
@@ -47,29 +52,23 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
   const int g = lane >> 2, t = lane & 3;
 
   // ---- global -> shared copy plan: 16-byte chunks, BK/2 per tile row --------------
+  // Thread tid copies chunk (row r0 + i*RPT, columns c2, c2+1) of the A tile for i < A_CHUNKS and of the B tile for
+  // i < B_CHUNKS.  Only the (gathered) A row indices are kept, as 32-bit integers: the kernel lives on a 64-register
+  // budget (4 CTAs per SM) and pointers would cost twice as much.
   constexpr int CPR = BK / 2;                       // chunks per row
+  constexpr int RPT = THREADS / CPR;                // tile rows covered by one pass of the CTA
   constexpr int A_CHUNKS = BM * CPR / THREADS;      // per thread
   constexpr int B_CHUNKS = BN * CPR / THREADS;
-  static_assert((BM * CPR) % THREADS == 0 && (BN * CPR) % THREADS == 0, "tile/threads mismatch");
-  const double* a_src[A_CHUNKS];
-  const double* b_src[B_CHUNKS];
-  int a_dst[A_CHUNKS], b_dst[B_CHUNKS];
+  static_assert((BM * CPR) % THREADS == 0 && (BN * CPR) % THREADS == 0 && THREADS % CPR == 0, "tile/threads mismatch");
+  const int r0 = tid / CPR;
+  const int kc_of_thread = 2 * (tid % CPR);         // same column offset for every chunk of this thread
+  int a_row[A_CHUNKS];
 #pragma unroll
   for (int i = 0; i < A_CHUNKS; ++i) {
-    const int id = tid + i * THREADS, r = id / CPR, c = id % CPR;
-    int n = min(n0 + r, N - 1);
+    int n = min(n0 + r0 + i * RPT, N - 1);
     if (a.rowsA) n = a.rowsA[n];
-    a_src[i] = a.A + (size_t)n * a.lda + 2 * c;
-    a_dst[i] = r * LDS + 2 * c;
+    a_row[i] = n;
   }
-#pragma unroll
-  for (int i = 0; i < B_CHUNKS; ++i) {
-    const int id = tid + i * THREADS, r = id / CPR, c = id % CPR;
-    const int m = min(m0 + r, a.M - 1);
-    b_src[i] = a.B + (size_t)m * a.ldb + 2 * c;
-    b_dst[i] = r * LDS + 2 * c;
-  }
-  const int kc_of_thread = 2 * (tid % CPR);         // same column offset for every chunk of this thread
   // Banded operator: B[m][k] is (numerically) zero for |m - k| > band, so this column tile only needs
   // k in [m0 - band, m0 + BN + band).  band <= 0: dense.
   int kt_lo = 0, KT = (a.K + BK - 1) / BK;
@@ -78,18 +77,31 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
     KT = min(KT, (min(a.K, m0 + BN + a.band) + BK - 1) / BK);
   }
 
+  // Ragged band: the k range above is the union over the BN columns of the tile, but the 8 columns of MMA tile j
+  // of this warp only need k in [mj - band, mj + 8 + band), mj = m0 + wn*WN + 8j.  In units of 8-wide k steps tile j
+  // is active for lo0 + j <= step < hi0 + j (mj advances one step per tile), so at the two ends of the k loop a
+  // warp issues only the DMMAs whose operator entries are not negligible: 8 + 2*band instead of BN + 2*band
+  // contraction steps per output column (260 instead of 316 at band 126: the DMMA pipe is what bounds this kernel).
+  int lo0 = -(1 << 28), hi0 = 1 << 28;
+  if (a.band > 0 && !g_no_ragged_dev) {
+    const int mw = m0 + wn * Cfg::WN;
+    lo0 = (mw - a.band) >> 3;                      // arithmetic shift = floor division (mw - band may be negative)
+    hi0 = (mw + 8 + a.band + 7) >> 3;
+  }
+
   auto load_stage = [&](int kt) {
     const int st = kt % STAGES;
     const int k0 = kt * BK;
     int bytes = (a.K - (k0 + kc_of_thread)) * 8;
     bytes = max(0, min(16, bytes));
-    const int koff = (bytes > 0) ? k0 : 0;          // keep the address in bounds when fully masked
-    double* as = As + st * BM * LDS;
-    double* bs = Bs + st * BN * LDS;
+    const int koff = ((bytes > 0) ? k0 : 0) + kc_of_thread;   // keep the address in bounds when fully masked
+    double* as = As + st * BM * LDS + r0 * LDS + kc_of_thread;
+    double* bs = Bs + st * BN * LDS + r0 * LDS + kc_of_thread;
 #pragma unroll
-    for (int i = 0; i < A_CHUNKS; ++i) cp_async16(as + a_dst[i], a_src[i] + koff, bytes);
+    for (int i = 0; i < A_CHUNKS; ++i) cp_async16(as + i * RPT * LDS, a.A + (size_t)a_row[i] * a.lda + koff, bytes);
 #pragma unroll
-    for (int i = 0; i < B_CHUNKS; ++i) cp_async16(bs + b_dst[i], b_src[i] + koff, bytes);
+    for (int i = 0; i < B_CHUNKS; ++i)
+      cp_async16(bs + i * RPT * LDS, a.B + (size_t)min(m0 + r0 + i * RPT, a.M - 1) * a.ldb + koff, bytes);
   };
 
   double acc[MT][NT][4];
@@ -118,6 +130,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
     const double* bs = Bs + (kt % STAGES) * BN * LDS + (wn * Cfg::WN) * LDS;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 8) {
+      const int step = kt * (BK / 8) + kk / 8;
+      const int j_hi = step - lo0, j_lo = step - hi0;     // MMA tile j is inside its band iff j_lo < j <= j_hi
+      if (j_hi < 0 || j_lo >= NT - 1) continue;           // warp-uniform: nothing of this warp's columns at this step
       double af[MT][4], bf[NT][2];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
@@ -127,16 +142,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
         af[i][2] = p[4];
         af[i][3] = p[8 * LDS + 4];
       }
+      if (j_hi >= NT - 1 && j_lo < 0) {                   // interior of the band: every tile
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const double* p = bs + (j * 8 + g) * LDS + kk + t;
-        bf[j][0] = p[0];
-        bf[j][1] = p[4];
+        for (int j = 0; j < NT; ++j) {
+          const double* p = bs + (j * 8 + g) * LDS + kk + t;
+          bf[j][0] = p[0];
+          bf[j][1] = p[4];
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma_16x8x8(acc[i][j], af[i], bf[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (j > j_lo && j <= j_hi) {
+            const double* p = bs + (j * 8 + g) * LDS + kk + t;
+            bf[j][0] = p[0];
+            bf[j][1] = p[4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) dmma_16x8x8(acc[i][j], af[i], bf[j]);
+          }
+        }
       }
-#pragma unroll
-      for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) dmma_16x8x8(acc[i][j], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
@@ -215,11 +243,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dgemm_nt_kernel(const
   pdl_trigger();    // late: the successor's CTAs are only parked for the moment the last tiles drain
 }
 
+static bool no_ragged_band();
+
 template <class Cfg>
 static int launch_gemm(const vgm_gemm_args& a, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     VGM_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    const int off = no_ragged_band() ? 1 : 0;
+    VGM_CUDA_OK(cudaMemcpyToSymbol(g_no_ragged_dev, &off, sizeof(int)));
     attr_set = true;
   }
   dim3 grid(ceil_div(a.M, Cfg::BN), ceil_div(a.N, Cfg::BM));
@@ -233,8 +265,13 @@ static int launch_gemm(const vgm_gemm_args& a, cudaStream_t s) {
 // short banded k loop leaves a large prologue/epilogue share, which more resident CTAs overlap.
 using CfgBig = GemmCfg<128, 128, 2, 4>;            // variant 0: 256 threads, warp tile 64x32, 1 CTA/SM
 using CfgV2 = GemmCfg<128, 64, 4, 2, 16, 3, 2>;    // variant 2: 256 threads, warp tile 32x32, 2 CTAs/SM
-using CfgV12 = GemmCfg<64, 64, 4, 2, 16, 2, 4>;    // variant 12 (default): 256 threads, warp tile 16x32, 4 CTAs/SM
-static int g_variant = 12;
+using CfgV12 = GemmCfg<64, 64, 4, 2, 16, 2, 4>;    // variant 12: 256 threads, warp tile 16x32, 4 CTAs/SM
+// Narrow column tiles for banded operators: all warps of a CTA work on the SAME 32 columns, so with the ragged band
+// they skip the same k steps (with 64-column tiles the two warp columns idle at opposite ends of the k loop) and
+// the CTA's own k range is BN + 2 band = 284 instead of 316 at band 126.
+using CfgV13 = GemmCfg<128, 32, 8, 1, 16, 2, 4>;   // variant 13: 256 threads, warp tile 16x32, 4 CTAs/SM
+using CfgV14 = GemmCfg<64, 32, 4, 1, 16, 2, 8>;    // variant 14 (default): 128 threads, warp tile 16x32, 8 CTAs/SM
+static int g_variant = 14;
 using CfgMid = GemmCfg<64, 64, 2, 2>;     // 128 threads, warp tile 32x32
 using CfgThin = GemmCfg<16, 64, 1, 4>;    // 128 threads, warp tile 16x16 (few rows: halo / tail solves)
 
@@ -242,7 +279,7 @@ int gemm_dot_tiles(int M, int N) {
   // number of column tiles (= partial dot products per row) the chosen configuration produces
   if (N <= 16) return ceil_div(M, CfgThin::BN);
   if ((long long)ceil_div(N, 128) * ceil_div(M, 128) < 120) return ceil_div(M, CfgMid::BN);
-  return ceil_div(M, g_variant == 0 ? CfgBig::BN : 64);
+  return ceil_div(M, g_variant == 0 ? CfgBig::BN : (g_variant == 2 || g_variant == 12) ? 64 : 32);
 }
 
 static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s);
@@ -255,10 +292,28 @@ static double banded_k_sum(int M, int K, int band, int bn) {
   return sum;
 }
 
+// The same with the ragged band of the kernel: every 8-column MMA tile runs its own range, in 8-wide k steps.
+static double ragged_k_sum(int M, int K, int band) {
+  if (band <= 0) return (double)ceil_div(M, 8) * K;
+  double sum = 0.0;
+  const int k_end = ceil_div(K, 8) * 8;
+  for (int m0 = 0; m0 < M; m0 += 8) {
+    const int lo = max(0, ((m0 - band) >> 3) * 8), hi = min(k_end, ((m0 + 8 + band + 7) >> 3) * 8);
+    sum += (double)(hi - lo);
+  }
+  return sum;
+}
+
+static bool no_ragged_band() {
+  static const bool off = getenv("VGM_NO_RAGGED_BAND") != nullptr;
+  return off;
+}
+
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s) {
   // executed flops (a banded operator skips the k range that is numerically zero) and compulsory bytes
   const int bn = 64;
-  const double flops = 2.0 * a.N * bn * banded_k_sum(a.M, a.K, a.band, bn);
+  const double flops = no_ragged_band() ? 2.0 * a.N * bn * banded_k_sum(a.M, a.K, a.band, bn)
+                                        : 2.0 * a.N * 8 * ragged_k_sum(a.M, a.K, a.band);
   const double bytes = 8.0 * ((double)a.N * a.K + (double)a.N * a.M);
   ProfScope prof(PROF_DGEMM, flops, bytes, s);
   return dgemm_dispatch(a, s);
@@ -275,7 +330,10 @@ static int dgemm_dispatch(const vgm_gemm_args& a, cudaStream_t s) {
   switch (g_variant) {
     case 0: return launch_gemm<CfgBig>(a, s);
     case 2: return launch_gemm<CfgV2>(a, s);
-    default: return launch_gemm<CfgV12>(a, s);
+    case 13: return launch_gemm<CfgV13>(a, s);
+    case 14: return launch_gemm<CfgV14>(a, s);
+    case 12: return launch_gemm<CfgV12>(a, s);
+    default: return launch_gemm<CfgV14>(a, s);
   }
 }
 
@@ -289,7 +347,7 @@ extern "C" int vgm_dgemm_nt(const vgm_gemm_args* args, vgm_stream_t stream) {
   return vgm::dgemm_nt(*args, (cudaStream_t)stream);
 }
 
-// Tuning knob (tile configuration of the large-N GEMM); 2 is the default.
+// Tuning knob (tile configuration of the large-N GEMM); 14 is the default.
 extern "C" int vgm_dgemm_set_variant(int v) {
   vgm::g_variant = v;
   return VGM_OK;

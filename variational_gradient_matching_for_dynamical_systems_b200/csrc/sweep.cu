@@ -33,6 +33,7 @@ namespace vgm {
 
 int dgemm_nt(const vgm_gemm_args& a, cudaStream_t s);
 int gemm_dot_tiles(int M, int N);
+constexpr int GEMM_MIN_BN = 32;   // narrowest column tile of any DMMA GEMM configuration (dgemm.cu)
 
 
 int program_state_assemble(const vgm_program* prog, const vgm_sweep_plan* pl, const double* X, const double* DX0,
@@ -276,7 +277,7 @@ struct PcgWs {
 
 static size_t pcg_ws_bytes(int n_hidden, int T, int ld) {
   const size_t mat = align_up((size_t)n_hidden * ld * sizeof(double), 256);
-  const int n_tiles = ceil_div(T, 64);  // upper bound over GEMM configurations
+  const int n_tiles = ceil_div(T, GEMM_MIN_BN);  // upper bound over GEMM configurations
   const size_t part = align_up((size_t)n_hidden * n_tiles * sizeof(double), 256);
   const size_t vec = align_up((size_t)n_hidden * sizeof(double), 256);
   return 5 * mat + ir_ws_bytes(n_hidden, ld) + small_solve_scratch_bytes(T) + 2 * part + 3 * vec +
@@ -288,7 +289,7 @@ static int pcg_carve(void* ws, size_t ws_bytes, int n_hidden, int T, int ld, Pcg
   VGM_REQUIRE(((uintptr_t)ws % 256) == 0, "workspace must be 256-byte aligned");
   char* p = (char*)ws;
   const size_t mat = align_up((size_t)n_hidden * ld * sizeof(double), 256);
-  const int n_tiles = ceil_div(T, 64);
+  const int n_tiles = ceil_div(T, GEMM_MIN_BN);
   const size_t part = align_up((size_t)n_hidden * n_tiles * sizeof(double), 256);
   const size_t vec = align_up((size_t)n_hidden * sizeof(double), 256);
   CgBuf& c = w.cb;
@@ -553,7 +554,7 @@ static int ir_solve(const vgm_operators* ops, const double* Lambda, const double
   const __nv_bfloat16* M_lo = M_hi + (size_t)T * ld;
   VGM_TRY(ir_async_init());
   IrAsync& as = g_ir_async;
-  const int dot_ld = ceil_div(T, 64);                    // row stride of pq_part (its allocation bound)
+  const int dot_ld = ceil_div(T, GEMM_MIN_BN);           // row stride of pq_part (its allocation bound)
 
   const int n_chunks = max(1, min(ir_chunk_target(), n_rows / IR_CHUNK_MIN_ROWS));
   IrChunk ch[IR_MAX_CHUNKS];

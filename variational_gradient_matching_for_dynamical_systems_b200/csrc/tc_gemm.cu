@@ -31,19 +31,33 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_TILE_BYTES = 128 * TC_BK * 2;                 // one 128 x 64 bf16 operand tile (A or B part)
 constexpr int TC_TMEM_COLS = 2 * TC_BN;
 constexpr int TC_OUT_TILE_BYTES = 32 * 32 * 4;                 // one 32-row x 32-column FP32 chunk of the output
-constexpr int TC_OUT_STAGING = TC_EPI_WARPS * 2 * TC_OUT_TILE_BYTES;   // two chunks per epilogue warp (TMA store ring)
 constexpr int TC_BRES_KB = 4;                                  // k-blocks of B a CTA can keep resident
 // BRES ("B resident"): a CTA is bound to one column tile, loads the k-blocks of the operator that tile needs ONCE
 // and streams only the A operand; possible when the band leaves <= TC_BRES_KB k-blocks per tile.  It halves the
 // L2 -> SMEM traffic, which is what bounds the streaming variant on the narrow low-precision bands.
-template <bool SPLIT, bool BRES>
+// SLICED (split product with the operator resident): the ring holds single 16 KB A tiles -- p_hi and p_lo of a k-block
+// travel through separate slots with their own barriers -- instead of (p_hi, p_lo) pairs.  Beside 128 KB of resident
+// (M_hi, M_lo) tiles the pair layout had room for two stages, i.e. 64 KB in flight per SM with a refill only after
+// all twelve MMAs of a k-block: the kernel ran at the latency of that ring (4.0 us per row tile against a 2.8 us HBM
+// floor).  Five slots (80 KB; the TMA-store staging of the epilogue shrinks to one chunk per warp to make room) are
+// refilled after the eight MMAs that read p_hi and after the four that read p_lo.  VGM_TC_NO_SLICED=1 keeps the pairs.
+template <bool SPLIT, bool BRES, bool SLICED_ = false>
 struct TcCfg {
+  static constexpr bool SLICED = SLICED_;
+  static_assert(!SLICED || (SPLIT && BRES), "the sliced ring is the split product with resident operator tiles");
   static constexpr int PARTS = SPLIT ? 2 : 1;                  // (hi, lo) or hi only, for A and for B
-  static constexpr int STAGE_BYTES = (BRES ? 1 : 2) * PARTS * TC_TILE_BYTES;
-  static constexpr int STAGES = BRES ? (SPLIT ? 2 : 6) : (SPLIT ? 3 : 6);
+  static constexpr int STAGE_BYTES = SLICED ? TC_TILE_BYTES : (BRES ? 1 : 2) * PARTS * TC_TILE_BYTES;
+  static constexpr int STAGES = SLICED ? 5 : BRES ? (SPLIT ? 2 : 6) : (SPLIT ? 3 : 6);
   static constexpr int RES_BYTES = BRES ? TC_BRES_KB * PARTS * TC_TILE_BYTES : 0;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + RES_BYTES + TC_OUT_STAGING + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int OUT_BUFS = SLICED ? 1 : 2;              // TMA-store staging chunks per epilogue warp
+  static constexpr int OUT_STAGING = TC_EPI_WARPS * OUT_BUFS * TC_OUT_TILE_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + RES_BYTES + OUT_STAGING + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 232448, "more than 227 KB of shared memory");
 };
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,10 +153,10 @@ __device__ __forceinline__ void tc_k_range(int ct, int K, int band, int& kb_lo, 
   }
 }
 
-template <bool SPLIT, bool BRES>
+template <bool SPLIT, bool BRES, bool SLICED = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
-  using Cfg = TcCfg<SPLIT, BRES>;
+  using Cfg = TcCfg<SPLIT, BRES, SLICED>;
   constexpr int STAGES = Cfg::STAGES, PARTS = Cfg::PARTS;
   extern __shared__ unsigned char tc_smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -150,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
   // stage layout: [A0][A1 if split] ([B0][B1 if split] unless BRES), 16 KB each; BRES keeps [kb][B0][B1] after them
   unsigned char* b_res = smem + STAGES * Cfg::STAGE_BYTES;
   unsigned char* out_stage = b_res + Cfg::RES_BYTES;             // [EPI_WARPS][2][32 x 128 B], 128B-swizzled rows
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + TC_OUT_STAGING);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_STAGING);
   uint64_t* full_bar = bars;                                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;                        // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;                    // [2]
@@ -217,6 +231,16 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
         int kb_lo, kb_hi;
         tc_k_range(ct, a.K, a.band, kb_lo, kb_hi);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          if (SLICED) {                                   // one slot per part: p_hi, then p_lo
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], TC_TILE_BYTES);
+              tma_load_2d(smem + stage * TC_TILE_BYTES, part ? &maps.a1 : &maps.a0, &full_bar[stage], kb * TC_BK, rt * TC_BM);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            continue;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
@@ -251,6 +275,32 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
         const uint32_t tmem_d = tmem_base + acc * TC_BN;
         uint32_t accumulate = 0;
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          if (SLICED) {
+            unsigned char* bt = b_res + (kb - kb_lo) * PARTS * TC_TILE_BYTES;
+            const uint64_t b0 = make_sw128_desc(bt), b1 = make_sw128_desc(bt + TC_TILE_BYTES);
+            mbar_wait(&full_bar[stage], phase);           // p_hi landed: hi.hi and hi.lo
+            tc_fence_after();
+            const uint64_t a0 = make_sw128_desc(smem + stage * TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              tc_mma_bf16(tmem_d, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), TC_IDESC, accumulate);
+              accumulate = 1;
+            }
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              tc_mma_bf16(tmem_d, a0 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), TC_IDESC, 1u);
+            tc_commit(&empty_bar[stage]);                 // the slot is free once these eight MMAs have retired
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            mbar_wait(&full_bar[stage], phase);           // p_lo landed: lo.hi
+            tc_fence_after();
+            const uint64_t a1 = make_sw128_desc(smem + stage * TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              tc_mma_bf16(tmem_d, a1 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), TC_IDESC, 1u);
+            tc_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_wait(&full_bar[stage], phase);             // TMA landed this stage
           tc_fence_after();
           unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
@@ -308,7 +358,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
       // makes the row-per-thread writes bank-conflict free) and one lane hands it to a TMA store, so global
       // memory sees whole 128-byte lines; rows >= n_rows and columns >= M are clipped by the tensor map.
       const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16);
-      unsigned char* my_stage = out_stage + (warp - 2) * 2 * TC_OUT_TILE_BYTES;
+      unsigned char* my_stage = out_stage + (warp - 2) * Cfg::OUT_BUFS * TC_OUT_TILE_BYTES;
       if (a.out_bf16) {
         // bf16 output: two 32-column TMEM loads make one 64-column (128-byte) row chunk, same swizzle and TMA store
         float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};   // eight independent chains
@@ -320,7 +370,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
           tmem_ld32(taddr + c + 32, v1);
           const int m0 = ct * TC_BN + c;
           if (m0 >= a.M) continue;                          // uniform
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (lane == 0) bulk_wait_read<Cfg::OUT_BUFS - 1>();
           __syncwarp();
           unsigned char* sb = my_stage + epi_buf * TC_OUT_TILE_BYTES;
 #pragma unroll
@@ -346,7 +396,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) tma_store_2d(&maps.out, sb, m0, rt * TC_BM + q * 32);
-          epi_buf ^= 1;
+          epi_buf = (epi_buf + 1) % Cfg::OUT_BUFS;
         }
         if (dot) a.dot_out[(size_t)row * a.dot_ld + ct] = ((pa[0] + pb[0]) + (pa[1] + pb[1])) + ((pa[2] + pb[2]) + (pa[3] + pb[3]));
         tc_fence_before();
@@ -359,8 +409,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
         tmem_ld32(taddr + c, v);                          // warp-collective: executed by all lanes
         const int m0 = ct * TC_BN + c;
         if (m0 >= a.M) continue;                          // uniform
-        // the store that used this buffer two chunks ago must have read it (one newer store may be pending)
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // the store that last used this buffer must have read it (with two buffers one newer store may be pending)
+        if (lane == 0) bulk_wait_read<Cfg::OUT_BUFS - 1>();
         __syncwarp();
         unsigned char* sb = my_stage + epi_buf * TC_OUT_TILE_BYTES;
 #pragma unroll
@@ -370,7 +420,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) tma_store_2d(&maps.out, sb, m0, rt * TC_BM + q * 32);
-        epi_buf ^= 1;
+        epi_buf = (epi_buf + 1) % Cfg::OUT_BUFS;
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -456,12 +506,12 @@ static int make_bf16_map(CUtensorMap* map, const void* base, int rows, int cols,
   return make_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, TC_BK, box_rows);
 }
 
-template <bool SPLIT, bool BRES>
+template <bool SPLIT, bool BRES, bool SLICED = false>
 static int tc_launch(const TcMaps& maps, const TcGemmArgs& args, int n_sm, cudaStream_t s) {
-  using Cfg = TcCfg<SPLIT, BRES>;
+  using Cfg = TcCfg<SPLIT, BRES, SLICED>;
   static bool attr = false;
   if (!attr) {
-    VGM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<SPLIT, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    VGM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<SPLIT, BRES, SLICED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
   const int row_tiles = ceil_div(args.n_rows, TC_BM), col_tiles = ceil_div(args.M, TC_BN);
@@ -472,7 +522,7 @@ static int tc_launch(const TcMaps& maps, const TcGemmArgs& args, int n_sm, cudaS
   } else {
     grid = min(row_tiles * col_tiles, n_sm);
   }
-  VGM_CUDA_OK(launch_pdl(tc_gemm_kernel<SPLIT, BRES>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, maps, args));
+  VGM_CUDA_OK(launch_pdl(tc_gemm_kernel<SPLIT, BRES, SLICED>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, maps, args));
   return VGM_OK;
 }
 
@@ -535,8 +585,11 @@ int tc_gemm(const TcGemmArgs& args, cudaStream_t s) {
   const double bytes = (double)args.n_rows * args.K * 2.0 * (split ? 2.0 : 1.0) +
                        (double)args.n_rows * args.M * (args.out_bf16 ? 2.0 : 4.0);
   ProfScope prof(PROF_TCGEMM, flops, bytes, s);
-  if (tc_bres_ok(largs, n_sm))
-    return split ? tc_launch<true, true>(maps, largs, n_sm, s) : tc_launch<false, true>(maps, largs, n_sm, s);
+  if (tc_bres_ok(largs, n_sm)) {
+    static const bool no_sliced = getenv("VGM_TC_NO_SLICED") != nullptr;
+    if (split) return no_sliced ? tc_launch<true, true>(maps, largs, n_sm, s) : tc_launch<true, true, true>(maps, largs, n_sm, s);
+    return tc_launch<false, true>(maps, largs, n_sm, s);
+  }
   return split ? tc_launch<true, false>(maps, largs, n_sm, s) : tc_launch<false, false>(maps, largs, n_sm, s);
 }
 
