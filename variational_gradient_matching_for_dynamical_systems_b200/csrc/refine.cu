@@ -94,19 +94,35 @@ ir_inner_init_kernel(IrBuf b, const double* __restrict__ R, const double* __rest
   const size_t oj = (size_t)j * ld, os = (size_t)slot * ld;
   // same active list as in the previous correction: row j still belongs to the same system, lam32 / s16 are valid
   const bool remap = !n_dev || n_dev[2];
+  const bool vec = (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(Lambda)) & 15) == 0;
   IR_ROW_LOOP(i, T) {
     float4 r, lam, sv;
     float* rp = &r.x; float* lp = &lam.x; float* sp = &sv.x;
+    double rd[4], ld4[4];
+    if (vec) {                                   // 16-byte loads (a group may reach into the row padding, ld >= T rounded up to 4: masked below)
+      *reinterpret_cast<double2*>(rd) = *reinterpret_cast<const double2*>(R + os + i);
+      *reinterpret_cast<double2*>(rd + 2) = *reinterpret_cast<const double2*>(R + os + i + 2);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) rd[e] = (i + e < T) ? R[os + i + e] : 0.0;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const bool ok = i + e < T;
-      rp[e] = ok ? (float)(R[os + i + e] * inv) : 0.f;
+      rp[e] = ok ? (float)(rd[e] * inv) : 0.f;
     }
     if (remap) {
+      if (vec) {
+        *reinterpret_cast<double2*>(ld4) = *reinterpret_cast<const double2*>(Lambda + os + i);
+        *reinterpret_cast<double2*>(ld4 + 2) = *reinterpret_cast<const double2*>(Lambda + os + i + 2);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ld4[e] = (i + e < T) ? Lambda[os + i + e] : 0.0;
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const bool ok = i + e < T;
-        lp[e] = ok ? (float)Lambda[os + i + e] : 0.f;
+        lp[e] = ok ? (float)ld4[e] : 0.f;
         sp[e] = ok ? precond_scale(lp[e], (float)(shift + c), (float)c) : 0.f;
       }
       *reinterpret_cast<float4*>(b.lam32 + oj + i) = lam;
@@ -359,10 +375,32 @@ ir_finish_kernel(IrBuf b, double* __restrict__ P, double* __restrict__ X, const 
   const float* d = b.d32 + (size_t)j * ld;
   double* p = P + (size_t)slot * ld;
   double* x = X + (size_t)slot_state[slot] * ld;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const double v = p[t] + sig * (double)d[t];
-    p[t] = v;
-    x[t] = v;
+  if ((ld & 3) == 0) {
+    // 16-byte accesses for whole groups of four; a partial last group (T % 4 != 0) goes element by element
+    IR_ROW_LOOP(i, T) {
+      if (i + 4 > T) {
+        for (int t = i; t < T; ++t) {
+          const double v = p[t] + sig * (double)d[t];
+          p[t] = v;
+          x[t] = v;
+        }
+        continue;
+      }
+      const float4 dv = ld_f4(d + i);
+      double2 a = *reinterpret_cast<const double2*>(p + i), c = *reinterpret_cast<const double2*>(p + i + 2);
+      a.x += sig * (double)dv.x; a.y += sig * (double)dv.y;
+      c.x += sig * (double)dv.z; c.y += sig * (double)dv.w;
+      *reinterpret_cast<double2*>(p + i) = a;
+      *reinterpret_cast<double2*>(p + i + 2) = c;
+      *reinterpret_cast<double2*>(x + i) = a;
+      *reinterpret_cast<double2*>(x + i + 2) = c;
+    }
+  } else {
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const double v = p[t] + sig * (double)d[t];
+      p[t] = v;
+      x[t] = v;
+    }
   }
   pdl_trigger();
 }
