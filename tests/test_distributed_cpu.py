@@ -236,6 +236,19 @@ def _shift_worker(rank, world, port, K, outdir):
         hx(X)
         rows = np.concatenate([loc.owned, loc.halo_states])
         ok = sh == 2 and bool(torch.equal(X, Xg[torch.as_tensor(rows)]))
+        # the same exchange as include/vgm_b200.h documents it for vgm_comm_halo_exchange (pack pub_rows padded to
+        # n_pub -> all-gather -> X[halo_rows[i]] = gathered[halo_src[i]]), emulated with the tables HaloExchange
+        # hands to the C entry point (gloo all_gather stands in for ncclAllGather)
+        X2 = torch.zeros_like(X)
+        X2[:loc.n_owned] = Xg[torch.as_tensor(loc.owned)]
+        pub = torch.zeros((hx.n_pub, 5), dtype=torch.float64)
+        if len(hx.pub_rows_local):
+            pub[:len(hx.pub_rows_local)] = X2[torch.as_tensor(hx.pub_rows_local)]
+        parts = [torch.zeros_like(pub) for _ in range(world)]
+        dist.all_gather(parts, pub)
+        gathered = torch.cat(parts)
+        X2[torch.as_tensor(hx.halo_rows_local)] = gathered[torch.as_tensor(hx.src_flat)]
+        ok = ok and bool(torch.equal(X2, X))
         with open(os.path.join(outdir, "rank%d.txt" % rank), "w") as f:
             f.write("ok" if ok else "bad")
     finally:
