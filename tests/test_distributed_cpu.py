@@ -262,3 +262,29 @@ def test_halo_exchange_with_shifted_blocks_gloo_world2(tmp_path):
     mp.spawn(_shift_worker, args=(world, port, K, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d.txt" % r)).read() == "ok"
+
+
+def test_partition_properties_random_shapes():
+    """Property check over random (K, world, align, shift): every state has exactly one owner, `owner_of` inverts
+    `owned_states`, block boundaries sit on multiples of `align`, and block sizes differ by at most one aligned unit
+    (the quantities the halo tables and the C-ABI halo exchange are built from)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 4), st.integers(0, 40), st.integers(0, 6))
+    def check(world, align, extra, shift_units):
+        K = world * align * 2 + extra * align          # at least two aligned units per rank, K a multiple of align
+        bounds = block_bounds(K, world, align=align)
+        assert bounds[0] == 0 and bounds[-1] == K and all(b % align == 0 for b in bounds)
+        sizes = np.diff(bounds)
+        assert sizes.min() > 0 and sizes.max() - sizes.min() <= align
+        shift = shift_units * align
+        seen = np.zeros(K, dtype=int)
+        for r in range(world):
+            own = owned_states(bounds, r, K, shift)
+            assert len(own) == sizes[r]
+            seen[own] += 1
+            assert (owner_of(own, bounds, K, shift) == r).all()
+        assert (seen == 1).all()
+
+    check()
