@@ -11,8 +11,10 @@
 //
 // tcgen05 has no f64 kind, so FP64 tensor work on sm_100a is warp-level DMMA.  The B operand
 // (a T x T operator, 8 MB at T=1000) stays L2 resident; the A operand streams from HBM once
-// per column-tile sweep.  Operands are staged through a 4-deep cp.async ring in shared
-// memory with a +4 double row pad (conflict-free 64-bit fragment loads).
+// per column-tile sweep.  Operands are staged through a cp.async ring in shared memory (2 to 4
+// stages, per tile configuration) with a +4 double row pad (conflict-free 64-bit fragment loads).
+// Banded operators: a CTA loops over the k range its columns need and every 8-column MMA tile
+// issues only the DMMAs inside its own band (the "ragged band" below).
 #include <stdlib.h>
 
 #include "vgm_common.cuh"
